@@ -1,0 +1,158 @@
+/* ntx.h — C ABI of libntx.so: B200 (sm_100a) kernels for NeRF-Texture's per-ray-sample hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + a cudaStream_t, allocates
+ * nothing, never synchronises, and returns 0 on success or a negative ntx_status (no exceptions cross
+ * the ABI; ntx_last_error() gives the message of the calling thread's last failure).  The caller owns all
+ * buffers, exactly like the reference's natives, which write into caller-allocated tensors and return void.
+ * The device is the current CUDA context's.  Calls on distinct streams are thread-safe.
+ *
+ * Each function names the reference interface it replaces (paths relative to yihua7/NeRF-Texture).
+ * The Python packages gridencoder / ffmlp / shencoder / raymarching shipped in nerf_texture_b200/compat bind
+ * these with ctypes; INTEGRATION.md shows the binding a reference maintainer would add.
+ */
+#ifndef NTX_H_
+#define NTX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* ntx_stream_t; /* == cudaStream_t */
+
+typedef enum {
+    NTX_OK = 0,
+    NTX_ERR_INVALID_ARGUMENT = -1, /* reference: TORCH_CHECK / std::runtime_error -> RuntimeError in Python */
+    NTX_ERR_UNSUPPORTED = -2,      /* e.g. "GridEncoding: C must be 1, 2, 4, or 8." (gridencoder.cu:355) */
+    NTX_ERR_CUDA = -3,             /* launch / runtime failure (the reference never checks: SURVEY F8) */
+    NTX_ERR_WORKSPACE = -4
+} ntx_status;
+
+typedef enum { NTX_F32 = 0, NTX_F16 = 1, NTX_F64 = 2 } ntx_dtype;
+
+/* layouts of the [levels x samples x features] grid tensors */
+typedef enum {
+    NTX_LAYOUT_LBC = 0, /* [L,B,C]: the reference kernel's layout (gridencoder.cu:362) */
+    NTX_LAYOUT_BLC = 1  /* [B,L*C]: what grid_encode() returns after its permute (grid.py:52) — no extra copy */
+} ntx_grid_layout;
+
+const char* ntx_last_error(void);
+int ntx_version(void);
+/* 1 if the library was built with sm_100a SASS and the current device is CC 10.x */
+int ntx_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------------ gridencoder
+ * replaces grid_encode_forward / grid_encode_backward (gridencoder/src/gridencoder.h:12-13, gridencoder.cu:419,444)
+ *   inputs      [B,D] f32 in [0,1]           embeddings [n_entries,C] dtype      offsets [L+1] i32
+ *   outputs     [L,B,C] or [B,L*C] dtype     dy_dx [B, L*D*C] dtype (only if calc_grad_inputs)
+ *   S = log2(per_level_scale) as f32, H = base resolution, gridtype 0 hash / 1 tiled.
+ * D in {2,3}, C in {1,2,4,8}; anything else -> NTX_ERR_UNSUPPORTED (reference: std::runtime_error). */
+int ntx_grid_encode_forward(const float* inputs, const void* embeddings, const int* offsets, void* outputs,
+                            uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                            int calc_grad_inputs, void* dy_dx, uint32_t gridtype, int align_corners,
+                            int dtype, int out_layout, ntx_stream_t stream);
+/*   grad [L,B,C] or [B,L*C] dtype;  grad_embeddings [n_entries,C] dtype, zero-initialised by the caller (grid.py:74);
+ *   grad_inputs [B,D] dtype (only if calc_grad_inputs; needs the dy_dx saved by the forward) */
+int ntx_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings, const int* offsets,
+                             void* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                             int calc_grad_inputs, const void* dy_dx, void* grad_inputs, uint32_t gridtype,
+                             int align_corners, int dtype, int grad_layout, ntx_stream_t stream);
+/* test hooks: the per-level `scale` the device computes (gridencoder.cu:126) and the integer corner-index
+ * stream of one level, idx[b*2^D + corner] (0xffffffff for out-of-range samples) */
+int ntx_grid_level_scales(float S, uint32_t H, uint32_t L, float* scales_out, ntx_stream_t stream);
+int ntx_grid_debug_indices(const float* inputs, const int* offsets, uint32_t B, uint32_t D, uint32_t level, float S,
+                           uint32_t H, uint32_t gridtype, int align_corners, uint32_t* idx_out, ntx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ ffmlp
+ * replaces ffmlp_forward / ffmlp_inference / ffmlp_backward / allocate_splitk / free_splitk
+ * (ffmlp/src/ffmlp.h:8-14, ffmlp.cu:635,673,749,721,732).  All tensors fp16.
+ *   inputs [B,input_dim]   weights flat [hidden*input_dim + (num_layers-1)*hidden*hidden + output_dim*hidden],
+ *   each matrix row-major [out,in] (ffmlp.cu:632)   outputs [B,output_dim]   output_dim <= 16 is padded to 16
+ *   by the caller (ffmlp.py:118); B must be a multiple of 128 (ffmlp.py:157).
+ *   forward_buffer [num_layers,B,hidden] (training), backward_buffer likewise.  activation ids: ffmlp.cu:22-33.
+ * hidden_dim in {16,32,64,128}; 256 and anything else -> NTX_ERR_UNSUPPORTED. */
+int ntx_ffmlp_forward(const void* inputs, const void* weights, uint32_t B, uint32_t input_dim, uint32_t output_dim,
+                      uint32_t hidden_dim, uint32_t num_layers, uint32_t activation, uint32_t output_activation,
+                      void* forward_buffer, void* outputs, ntx_stream_t stream);
+int ntx_ffmlp_inference(const void* inputs, const void* weights, uint32_t B, uint32_t input_dim, uint32_t output_dim,
+                        uint32_t hidden_dim, uint32_t num_layers, uint32_t activation, uint32_t output_activation,
+                        void* inference_buffer /* unused, may be NULL */, void* outputs, ntx_stream_t stream);
+/* workspace: fp32 scratch for the weight-gradient reduction, ntx_ffmlp_backward_workspace_bytes() bytes */
+size_t ntx_ffmlp_backward_workspace_bytes(uint32_t input_dim, uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers);
+int ntx_ffmlp_backward(const void* grad, const void* inputs, const void* weights, const void* forward_buffer,
+                       uint32_t B, uint32_t input_dim, uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers,
+                       uint32_t activation, uint32_t output_activation, int calc_grad_inputs, void* backward_buffer,
+                       void* grad_inputs, void* grad_weights, void* workspace, ntx_stream_t stream);
+/* kept for drop-in parity with ffmlp.py:126,133 — the B200 path needs no side streams; both are no-ops */
+int ntx_allocate_splitk(size_t size);
+int ntx_free_splitk(void);
+
+/* ------------------------------------------------------------------------------------------------ shencoder
+ * replaces sh_encode_forward / sh_encode_backward (shencoder/src/shencoder.h:10,13, shencoder.cu:402,421).  fp32 only
+ * (the Python wrapper forces fp32: sphere_harmonics.py:16).  inputs [B,3], outputs [B,C*C], dy_dx [B,3*C*C], C in 1..8. */
+int ntx_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint32_t D, uint32_t C,
+                          int calc_grad_inputs, float* dy_dx, ntx_stream_t stream);
+/* grad_inputs [B,3] is ACCUMULATED into (shencoder.cu:377); the caller zero-fills it (sphere_harmonics.py:50) */
+int ntx_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, uint32_t D, uint32_t C,
+                           const float* dy_dx, float* grad_inputs, ntx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ raymarching
+ * replaces the natives of raymarching/src/raymarching.h:7-20 (fp32 / int32 / uint8 only; the Python wrappers cast
+ * everything to fp32: raymarching.py custom_fwd(cast_inputs=torch.float32)). */
+int ntx_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near,
+                           float* nears, float* fars, ntx_stream_t stream);
+int ntx_polar_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords, ntx_stream_t stream);
+int ntx_morton3D(const int* coords, uint32_t N, int* indices, ntx_stream_t stream);
+int ntx_morton3D_invert(const int* indices, uint32_t N, int* coords, ntx_stream_t stream);
+int ntx_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, ntx_stream_t stream);
+
+/* march_rays_train (raymarching.cu:485) and, with rays_ts != NULL, march_rays_train_differentiable (:680).
+ * counter [2] i32 = {samples, rays}: ADDED to, like the reference's atomicAdd; the caller zeroes it (renderer.py:367).
+ * Segments are allocated by an ordered scan, so rays[] rows and sample offsets come out in ascending ray order — a
+ * deterministic member of the reference's (atomic, arbitrary-order) outcome set.
+ * workspace: ntx_march_rays_train_workspace_bytes(N) bytes, zero on first use (the kernel leaves it zeroed). */
+size_t ntx_march_rays_train_workspace_bytes(uint32_t N);
+int ntx_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
+                         uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                         const float* fars, float* xyzs, float* dirs, float* deltas, float* rays_ts, int* rays,
+                         int* counter, uint32_t perturb, void* workspace, ntx_stream_t stream);
+int ntx_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int* rays,
+                                     uint32_t M, uint32_t N, float* weights_sum, float* depth, float* image,
+                                     ntx_stream_t stream);
+int ntx_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image, const float* sigmas,
+                                      const float* rgbs, const float* deltas, const int* rays, const float* weights_sum,
+                                      const float* image, uint32_t M, uint32_t N, float* grad_sigmas, float* grad_rgbs,
+                                      ntx_stream_t stream);
+/* inference loop body (raymarching.cu:1009,1107,1137).  xyzs/dirs/deltas must be zero-filled by the caller for slots
+ * that are not written (raymarching.py:389-391) unless zero_fill != 0, in which case the kernel writes the zeros itself
+ * (saves three memsets per loop iteration; M_padded = rows of xyzs/dirs/deltas). */
+int ntx_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, const float* rays_t, const float* rays_o,
+                   const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                   const uint8_t* grid, const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                   uint32_t perturb, int zero_fill, uint32_t M_padded, ntx_stream_t stream);
+int ntx_composite_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, float* rays_t, const float* sigmas,
+                       const float* rgbs, const float* deltas, float* weights_sum, float* depth, float* image,
+                       ntx_stream_t stream);
+/* compact_rays: survivors (rays_t_old >= 0) are written in ascending slot order (warp-ballot + block scan + chained
+ * look-back); alive_counter [1] is ADDED to.  workspace: ntx_compact_rays_workspace_bytes(n_alive), zero on first use. */
+size_t ntx_compact_rays_workspace_bytes(uint32_t n_alive);
+int ntx_compact_rays(uint32_t n_alive, int* rays_alive, const int* rays_alive_old, float* rays_t, const float* rays_t_old,
+                     int* alive_counter, void* workspace, ntx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ fused field
+ * One launch for nerf/network_ff.py:85-101 in fp16 inference mode:
+ *   x01 = (xyz+bound)/(2 bound) -> hash-grid (D=3, C=2, L<=16, fp16 table) -> FFMLP(2L -> 64 -> 16) -> sigma = exp(h0)*density_scale
+ *   SH(dirs, degree 4) ++ h[1..15] ++ 0 -> FFMLP(32 -> 64 -> 64 -> 16)[:3] -> sigmoid -> rgb
+ * Features, hidden activations and geo_feat never leave the SM (smem / TMEM); the two MLPs run on tcgen05.
+ * xyz, dirs [M,3] f32; sigmas [M] f32; rgbs [M,3] f32.  Rows whose deltas (optional, [M,2]) are 0 are skipped. */
+int ntx_ngp_field_forward(const float* xyz, const float* dirs, const float* deltas /* nullable */, uint32_t M, float bound,
+                          const void* embeddings_f16, const int* offsets, uint32_t L, float S, uint32_t H,
+                          int align_corners, const void* w_sigma_f16, const void* w_color_f16, float density_scale,
+                          float* sigmas, float* rgbs, ntx_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTX_H_ */

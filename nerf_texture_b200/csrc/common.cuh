@@ -1,0 +1,77 @@
+// common.cuh — shared host/device helpers for libntx (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <algorithm>
+
+#include "../../include/ntx.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libntx is written for sm_100a (B200) only"
+#endif
+
+namespace ntx {
+
+constexpr int kNumSMs = 148;  // B200
+
+void set_error(const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return NTX_ERR_CUDA;
+    }
+    return NTX_OK;
+}
+
+#define NTX_REQUIRE(cond, code, ...)        \
+    do {                                    \
+        if (!(cond)) {                      \
+            ::ntx::set_error(__VA_ARGS__);  \
+            return (code);                  \
+        }                                   \
+    } while (0)
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+// ---- cache-hinted accesses ---------------------------------------------------------------------------
+// streaming (read-once) 128-bit load that does not pollute L1
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_u4(void* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream_u2(void* p, const uint2& v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_stream_f32(float* p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+// table gather: read-only path, keep in L1 (tables are re-read by neighbouring samples)
+__device__ __forceinline__ uint32_t ld_table_u32(const void* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float2 half2_bits_to_float2(uint32_t v) {
+    __half2 h = *reinterpret_cast<__half2*>(&v);
+    return __half22float2(h);
+}
+__device__ __forceinline__ uint32_t float2_to_half2_bits(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+}  // namespace ntx

@@ -1,0 +1,662 @@
+// raymarch.cu — occupancy-grid ray marching, compositing and ray compaction for sm_100a.
+// Replaces raymarching/src/raymarching.cu of the reference.  Arithmetic per ray is the reference's; what changes:
+//   * every place the reference claims output space with a global atomicAdd per ray (march_rays_train :408-409,
+//     compact_rays :1130) uses a warp-shuffle / block scan + decoupled look-back across blocks instead, so segment
+//     offsets and compacted rays come out in ascending order: deterministic, and adjacent slots stay adjacent
+//     rays, which keeps the downstream hash-grid gather coherent;
+//   * march_rays can zero its own unused slots (saves three cudaMemset per render-loop iteration);
+//   * launches go to the caller's stream and are error-checked.
+#include "common.cuh"
+
+namespace ntx {
+
+__device__ __forceinline__ float clampf(const float x, const float lo, const float hi) { return fminf(hi, fmaxf(lo, x)); }
+__device__ __forceinline__ float signf1(const float x) { return copysignf(1.0f, x); }
+constexpr float kSqrt3 = 1.7320508075688772f;
+constexpr float kRPi = 0.3183098861837907f;
+
+// raymarching.cu:44-56
+__device__ __forceinline__ int mip_from_pos(const float x, const float y, const float z, const float max_cascade) {
+    const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+    int exponent;
+    frexpf(mx, &exponent);
+    return (int)fminf(max_cascade - 1, fmaxf(0, exponent));
+}
+__device__ __forceinline__ int mip_from_dt(const float dt, const float H, const float max_cascade) {
+    const float mx = dt * H * 0.5;
+    int exponent;
+    frexpf(mx, &exponent);
+    return (int)fminf(max_cascade - 1, fmaxf(0, exponent));
+}
+// raymarching.cu:58-83
+__host__ __device__ __forceinline__ uint32_t expand_bits(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__host__ __device__ __forceinline__ uint32_t morton3D_1(uint32_t x, uint32_t y, uint32_t z) { return expand_bits(x) | (expand_bits(y) << 1) | (expand_bits(z) << 2); }
+__host__ __device__ __forceinline__ uint32_t morton3D_invert_1(uint32_t x) {
+    x = x & 0x49249249;
+    x = (x | (x >> 2)) & 0xc30c30c3;
+    x = (x | (x >> 4)) & 0x0f00f00f;
+    x = (x | (x >> 8)) & 0xff0000ff;
+    x = (x | (x >> 16)) & 0x0000ffff;
+    return x;
+}
+
+// PCG-XSH-RR 64/32 (pcg32.h:44-170)
+struct Pcg32 {
+    uint64_t state, inc;
+    static constexpr uint64_t kMult = 0x5851f42d4c957f2dULL;
+    __device__ __forceinline__ uint32_t next_uint() {
+        const uint64_t old = state;
+        state = old * kMult + inc;
+        const uint32_t xorshifted = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+        const uint32_t rot = (uint32_t)(old >> 59u);
+        return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31));
+    }
+    __device__ __forceinline__ void seed(uint64_t initstate, uint64_t initseq = 1) {
+        state = 0U; inc = (initseq << 1u) | 1u;
+        next_uint(); state += initstate; next_uint();
+    }
+    __device__ __forceinline__ float next_float() { return __uint_as_float((next_uint() >> 9) | 0x3f800000u) - 1.0f; }
+    __device__ __forceinline__ void advance(uint64_t delta) {
+        uint64_t cur_mult = kMult, cur_plus = inc, acc_mult = 1u, acc_plus = 0u;
+        while (delta > 0) {
+            if (delta & 1) { acc_mult *= cur_mult; acc_plus = acc_plus * cur_mult + cur_plus; }
+            cur_plus = (cur_mult + 1) * cur_plus;
+            cur_mult *= cur_mult;
+            delta /= 2;
+        }
+        state = acc_mult * state + acc_plus;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------- DDA probe
+struct Ray {
+    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
+};
+struct MarchParams {
+    float bound, dt_gamma, dt_min, dt_max, rH;
+    uint32_t C, H;
+    const uint8_t* __restrict__ grid;
+};
+
+__device__ __forceinline__ MarchParams make_march_params(float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid) {
+    MarchParams p;
+    p.bound = bound; p.dt_gamma = dt_gamma;
+    p.dt_min = 2 * kSqrt3 / max_steps;               // raymarching.cu:346
+    p.dt_max = 2 * kSqrt3 * (1 << (C - 1)) / H;      // :347
+    p.rH = 1 / (float)H;
+    p.C = C; p.H = H; p.grid = grid;
+    return p;
+}
+__device__ __forceinline__ Ray load_ray(const float* __restrict__ o, const float* __restrict__ d) {
+    Ray r;
+    r.ox = o[0]; r.oy = o[1]; r.oz = o[2]; r.dx = d[0]; r.dy = d[1]; r.dz = d[2];
+    r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
+    return r;
+}
+
+// One step of the marcher (raymarching.cu:362-402).  Returns true if the voxel containing t is occupied (x,y,z,dt valid);
+// otherwise advances t to the first dt-quantised position beyond the voxel.
+__device__ __forceinline__ bool probe(const Ray& r, const MarchParams& p, float& t, float& x, float& y, float& z, float& dt) {
+    x = clampf(r.ox + t * r.dx, -p.bound, p.bound);
+    y = clampf(r.oy + t * r.dy, -p.bound, p.bound);
+    z = clampf(r.oz + t * r.dz, -p.bound, p.bound);
+    dt = clampf(t * p.dt_gamma, p.dt_min, p.dt_max);
+    const int level = max(mip_from_pos(x, y, z, p.C), mip_from_dt(dt, p.H, p.C));
+    const float mip_bound = fminf((float)(1 << level), p.bound);
+    const float mip_rbound = 1 / mip_bound;
+    const int nx = clampf(0.5 * (x * mip_rbound + 1) * p.H, 0.0f, (float)(p.H - 1));
+    const int ny = clampf(0.5 * (y * mip_rbound + 1) * p.H, 0.0f, (float)(p.H - 1));
+    const int nz = clampf(0.5 * (z * mip_rbound + 1) * p.H, 0.0f, (float)(p.H - 1));
+    const uint32_t index = level * p.H * p.H * p.H + morton3D_1(nx, ny, nz);
+    const bool occ = p.grid[index / 8] & (1 << (index % 8));
+    if (occ) return true;
+    const float tx = (((nx + 0.5f + 0.5f * signf1(r.dx)) * p.rH * 2 - 1) * mip_bound - x) * r.rdx;
+    const float ty = (((ny + 0.5f + 0.5f * signf1(r.dy)) * p.rH * 2 - 1) * mip_bound - y) * r.rdy;
+    const float tz = (((nz + 0.5f + 0.5f * signf1(r.dz)) * p.rH * 2 - 1) * mip_bound - z) * r.rdz;
+    const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+    do { t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max); } while (t < tt);
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------------- ordered grid-wide scan
+// Workspace layout: u32 ticket, u32 done, then one u64 status word per block:
+//   bits 63..62: 0 = nothing yet, 1 = block aggregate, 2 = inclusive prefix;  bits 61..0: value.
+// Blocks take dynamic tickets so that a block only ever waits on blocks that are already running.
+struct ScanWS { uint32_t ticket, done; unsigned long long state[1]; };
+constexpr unsigned long long kScanAgg = 1ull << 62, kScanIncl = 2ull << 62, kScanMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// block-wide exclusive scan of one value per thread (blockDim.x <= 1024, multiple of 32); returns exclusive prefix, total in `total`
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t& total, uint32_t* warp_sums /* smem[32] */) {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t s = lane < nw ? warp_sums[lane] : 0, si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, si, o); if (lane >= o) si += n; }
+        warp_sums[lane] = si - s;  // exclusive prefix of warp sums
+        if (lane == 31) warp_sums[32] = si;
+    }
+    __syncthreads();
+    total = warp_sums[32];
+    const uint32_t r = warp_sums[wid] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+// called by all threads of the block; returns the exclusive prefix of `agg` over blocks in ticket order (+ base for everything).
+// `base` only needs to be valid in the block holding ticket 0.
+__device__ __forceinline__ unsigned long long chained_prefix(ScanWS* ws, uint32_t ticket, unsigned long long agg, unsigned long long base,
+                                                             unsigned long long* smem_bcast) {
+    if (threadIdx.x < 32) {
+        const uint32_t lane = threadIdx.x;
+        unsigned long long excl = 0;
+        if (ticket == 0) {
+            excl = base;
+            if (lane == 0) st_release_u64(&ws->state[0], kScanIncl | (base + agg));
+        } else {
+            if (lane == 0) st_release_u64(&ws->state[ticket], kScanAgg | agg);
+            int j = (int)ticket - 1;
+            while (true) {
+                const int idx = j - (int)lane;
+                unsigned long long s = kScanIncl;  // virtual predecessor of block 0 (never selected: block 0 is inclusive)
+                if (idx >= 0) { do { s = ld_acquire_u64(&ws->state[idx]); } while ((s >> 62) == 0); }
+                const uint32_t incl = __ballot_sync(0xffffffffu, (s >> 62) == 2);
+                const int first = incl ? (__ffs(incl) - 1) : 31;
+                unsigned long long val = ((int)lane <= first) ? (s & kScanMask) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+                excl += val;
+                if (incl) break;
+                j -= 32;
+            }
+            if (lane == 0) st_release_u64(&ws->state[ticket], kScanIncl | (excl + agg));
+        }
+        if (lane == 0) *smem_bcast = excl;
+    }
+    __syncthreads();
+    const unsigned long long r = *smem_bcast;
+    __syncthreads();
+    return r;
+}
+
+// every block calls this once at its very end; the last block to arrive restores the workspace to all-zero
+__device__ __forceinline__ void scan_ws_release(ScanWS* ws, uint32_t nblocks) {
+    __syncthreads();
+    __shared__ uint32_t s_last;
+    if (threadIdx.x == 0) { __threadfence(); s_last = (atomicAdd(&ws->done, 1u) == nblocks - 1) ? 1u : 0u; }
+    __syncthreads();
+    if (s_last) {
+        for (uint32_t i = threadIdx.x; i < nblocks; i += blockDim.x) ws->state[i] = 0ull;
+        if (threadIdx.x == 0) { ws->ticket = 0; ws->done = 0; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- small utilities
+__global__ void __launch_bounds__(128) near_far_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ aabb,
+                                                       const uint32_t N, const float min_near, float* __restrict__ nears, float* __restrict__ fars) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float rdx = 1 / rays_d[n * 3], rdy = 1 / rays_d[n * 3 + 1], rdz = 1 / rays_d[n * 3 + 2];
+    float near = (aabb[0] - ox) * rdx, far = (aabb[3] - ox) * rdx;
+    if (near > far) { const float c = near; near = far; far = c; }
+    float near_y = (aabb[1] - oy) * rdy, far_y = (aabb[4] - oy) * rdy;
+    if (near_y > far_y) { const float c = near_y; near_y = far_y; far_y = c; }
+    if (near > far_y || near_y > far) { nears[n] = fars[n] = 3.402823466e+38f; return; }
+    if (near_y > near) near = near_y;
+    if (far_y < far) far = far_y;
+    float near_z = (aabb[2] - oz) * rdz, far_z = (aabb[5] - oz) * rdz;
+    if (near_z > far_z) { const float c = near_z; near_z = far_z; far_z = c; }
+    if (near > far_z || near_z > far) { nears[n] = fars[n] = 3.402823466e+38f; return; }
+    if (near_z > near) near = near_z;
+    if (far_z < far) far = far_z;
+    if (near < min_near) near = min_near;
+    nears[n] = near;
+    fars[n] = far;
+}
+
+__global__ void __launch_bounds__(128) polar_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float radius, const uint32_t N,
+                                                    float* __restrict__ coords) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float dx = rays_d[n * 3], dy = rays_d[n * 3 + 1], dz = rays_d[n * 3 + 2];
+    const float A = dx * dx + dy * dy + dz * dz;
+    const float Bq = ox * dx + oy * dy + oz * dz;
+    const float Cq = ox * ox + oy * oy + oz * oz - radius * radius;
+    const float t = (-Bq + sqrtf(Bq * Bq - A * Cq)) / A;
+    const float x = ox + t * dx, y = oy + t * dy, z = oz + t * dz;
+    const float theta = atan2(sqrtf(x * x + z * z), y);
+    const float phi = atan2(z, x);
+    coords[n * 2] = 2 * theta * kRPi - 1;
+    coords[n * 2 + 1] = phi * kRPi;
+}
+
+__global__ void __launch_bounds__(128) morton3D_kernel(const int* __restrict__ coords, const uint32_t N, int* __restrict__ indices) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    indices[n] = morton3D_1(coords[n * 3], coords[n * 3 + 1], coords[n * 3 + 2]);
+}
+__global__ void __launch_bounds__(128) morton3D_invert_kernel(const int* __restrict__ indices, const uint32_t N, int* __restrict__ coords) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const int ind = indices[n];
+    coords[n * 3] = morton3D_invert_1(ind >> 0);
+    coords[n * 3 + 1] = morton3D_invert_1(ind >> 1);
+    coords[n * 3 + 2] = morton3D_invert_1(ind >> 2);
+}
+
+// 8 densities -> 1 byte (raymarching.cu:270-291); each thread packs 32 densities (one 32-bit word) with 128-bit loads
+__global__ void __launch_bounds__(256) packbits_kernel(const float* __restrict__ grid, const uint32_t N, const float thresh, uint8_t* __restrict__ bitfield) {
+    const uint32_t words = N / 4;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
+        const uint4* src = reinterpret_cast<const uint4*>(grid + (size_t)w * 32);
+        uint32_t bits = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const uint4 v = ld_stream_u4(src + q);
+            bits |= (__uint_as_float(v.x) > thresh ? 1u : 0u) << (q * 4 + 0);
+            bits |= (__uint_as_float(v.y) > thresh ? 1u : 0u) << (q * 4 + 1);
+            bits |= (__uint_as_float(v.z) > thresh ? 1u : 0u) << (q * 4 + 2);
+            bits |= (__uint_as_float(v.w) > thresh ? 1u : 0u) << (q * 4 + 3);
+        }
+        reinterpret_cast<uint32_t*>(bitfield)[w] = bits;
+    }
+    // tail bytes (N not a multiple of 4) and unaligned inputs are handled by the scalar kernel below
+}
+__global__ void __launch_bounds__(128) packbits_scalar_kernel(const float* __restrict__ grid, const uint32_t n0, const uint32_t N, const float thresh,
+                                                              uint8_t* __restrict__ bitfield) {
+    const uint32_t n = n0 + threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    uint8_t bits = 0;
+#pragma unroll
+    for (uint8_t i = 0; i < 8; i++) bits |= (grid[(size_t)n * 8 + i] > thresh) ? ((uint8_t)1 << i) : 0;
+    bitfield[n] = bits;
+}
+
+// ---------------------------------------------------------------------------------------------------- training marcher
+constexpr int kTrainThreads = 128;
+
+__global__ void __launch_bounds__(kTrainThreads) march_rays_train_kernel(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid, const float bound, const float dt_gamma,
+    const uint32_t max_steps, const uint32_t N, const uint32_t C, const uint32_t H, const uint32_t M, const float* __restrict__ nears,
+    const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas, float* __restrict__ rays_ts,
+    int* __restrict__ rays, int* __restrict__ counter, const uint32_t perturb, ScanWS* ws) {
+    __shared__ uint32_t s_ticket;
+    __shared__ uint32_t s_warp[33];
+    __shared__ unsigned long long s_bcast;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&ws->ticket, 1u);
+    __syncthreads();
+    const uint32_t ticket = s_ticket;
+    const uint32_t n = ticket * kTrainThreads + threadIdx.x;
+    const bool valid = n < N;
+    const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H, grid);
+
+    Ray r{};
+    float far = 0.f, t0 = 0.f;
+    uint32_t num_steps = 0;
+    if (valid) {
+        r = load_ray(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
+        far = fars[n];
+        t0 = nears[n];
+        if (perturb) {
+            Pcg32 rng; rng.seed(42);          // hard-coded seed, raymarching.cu:488
+            rng.advance(n);
+            t0 += p.dt_min * rng.next_float();
+        }
+        // pass 1: count the occupied steps (:362-403)
+        float t = t0, x, y, z, dt;
+        while (t < far && num_steps < max_steps) {
+            if (probe(r, p, t, x, y, z, dt)) { num_steps++; t += dt; }
+        }
+    }
+    // ordered allocation of the output segment (replaces the two atomicAdds at :408-409)
+    uint32_t block_total;
+    const uint32_t local = block_exclusive_scan(num_steps, block_total, s_warp);
+    const unsigned long long base = (ticket == 0) ? (unsigned long long)(uint32_t)counter[0] : 0ull;
+    const unsigned long long excl = chained_prefix(ws, ticket, block_total, base, &s_bcast);
+    const uint32_t nblocks = gridDim.x;
+    if (ticket == nblocks - 1 && threadIdx.x == 0) {
+        // excl already contains the caller's starting value of counter[0]
+        const uint32_t ray_base = (uint32_t)counter[1];
+        counter[0] = (int)(uint32_t)(excl + block_total);
+        counter[1] = (int)(ray_base + N);
+    }
+    if (valid) {
+        const uint32_t point_index = (uint32_t)excl + local;
+        // NOTE: the reference adds counter[1]'s starting value to the row index; callers always pass 0 (renderer.py:367),
+        // and a non-zero start would index rays[] out of bounds there, so row == n here.
+        rays[(size_t)n * 3] = (int)n;
+        rays[(size_t)n * 3 + 1] = (int)point_index;
+        rays[(size_t)n * 3 + 2] = (int)num_steps;
+        if (num_steps != 0 && point_index + num_steps < M) {   // :418-419
+            float* px = xyzs + (size_t)point_index * 3;
+            float* pd = dirs + (size_t)point_index * 3;
+            float* pl = deltas + (size_t)point_index * 2;
+            float* pt = rays_ts ? rays_ts + point_index : nullptr;
+            float t = t0, last_t = t0, x, y, z, dt;
+            uint32_t step = 0;
+            while (t < far && step < num_steps) {               // pass 2 (:430-482)
+                if (probe(r, p, t, x, y, z, dt)) {
+                    px[0] = x; px[1] = y; px[2] = z;
+                    pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+                    t += dt;
+                    pl[0] = dt; pl[1] = t - last_t;
+                    if (pt) { pt[0] = t; pt++; }
+                    last_t = t;
+                    px += 3; pd += 3; pl += 2; step++;
+                }
+            }
+        }
+    }
+    scan_ws_release(ws, nblocks);
+}
+
+// raymarching.cu:700-777
+__global__ void __launch_bounds__(128) composite_train_fwd_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                                                                  const int* __restrict__ rays, const uint32_t M, const uint32_t N,
+                                                                  float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const uint32_t index = rays[n * 3], offset = rays[n * 3 + 1], num_steps = rays[n * 3 + 2];
+    if (num_steps == 0 || offset + num_steps >= M) {
+        weights_sum[index] = 0; depth[index] = 0;
+        image[index * 3] = 0; image[index * 3 + 1] = 0; image[index * 3 + 2] = 0;
+        return;
+    }
+    sigmas += offset; rgbs += (size_t)offset * 3; deltas += (size_t)offset * 2;
+    float T = 1.0f, r = 0, g = 0, b = 0, ws = 0, t = 0, d = 0;
+    for (uint32_t step = 0; step < num_steps; step++) {
+        const float alpha = 1.0f - __expf(-sigmas[0] * deltas[0]);
+        const float weight = alpha * T;
+        r += weight * rgbs[0]; g += weight * rgbs[1]; b += weight * rgbs[2];
+        t += deltas[1];
+        d += weight * t;
+        ws += weight;
+        T *= 1.0f - alpha;
+        sigmas++; rgbs += 3; deltas += 2;
+    }
+    weights_sum[index] = ws; depth[index] = d;
+    image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
+}
+
+// raymarching.cu:802-881
+__global__ void __launch_bounds__(128) composite_train_bwd_kernel(const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image,
+                                                                  const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                                                                  const int* __restrict__ rays, const float* __restrict__ weights_sum, const float* __restrict__ image,
+                                                                  const uint32_t M, const uint32_t N, float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const uint32_t index = rays[n * 3], offset = rays[n * 3 + 1], num_steps = rays[n * 3 + 2];
+    if (num_steps == 0 || offset + num_steps >= M) return;
+    const float gws = grad_weights_sum[index];
+    const float gi0 = grad_image[index * 3], gi1 = grad_image[index * 3 + 1], gi2 = grad_image[index * 3 + 2];
+    const float r_final = image[index * 3], g_final = image[index * 3 + 1], b_final = image[index * 3 + 2], ws_final = weights_sum[index];
+    sigmas += offset; rgbs += (size_t)offset * 3; deltas += (size_t)offset * 2; grad_sigmas += offset; grad_rgbs += (size_t)offset * 3;
+    float T = 1.0f, r = 0, g = 0, b = 0, ws = 0;
+    for (uint32_t step = 0; step < num_steps; step++) {
+        const float alpha = 1.0f - __expf(-sigmas[0] * deltas[0]);
+        const float weight = alpha * T;
+        r += weight * rgbs[0]; g += weight * rgbs[1]; b += weight * rgbs[2];
+        ws += weight;
+        T *= 1.0f - alpha;
+        grad_rgbs[0] = gi0 * weight; grad_rgbs[1] = gi1 * weight; grad_rgbs[2] = gi2 * weight;
+        grad_sigmas[0] = deltas[0] * (gi0 * (T * rgbs[0] - (r_final - r)) + gi1 * (T * rgbs[1] - (g_final - g)) + gi2 * (T * rgbs[2] - (b_final - b)) +
+                                      gws * (T - (ws_final - ws)));
+        sigmas++; rgbs += 3; deltas += 2; grad_sigmas++; grad_rgbs += 3;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- inference loop body
+// raymarching.cu:900-1006
+__global__ void __launch_bounds__(128) march_rays_kernel(const uint32_t n_alive, const uint32_t n_step, const int* __restrict__ rays_alive,
+                                                         const float* __restrict__ rays_t, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                         const float bound, const float dt_gamma, const uint32_t max_steps, const uint32_t C, const uint32_t H,
+                                                         const uint8_t* __restrict__ grid, const float* __restrict__ nears, const float* __restrict__ fars,
+                                                         float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas, const uint32_t perturb,
+                                                         const int zero_fill, const uint32_t M_padded) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (zero_fill) {
+        // padding rows beyond n_alive*n_step (align-to-128 tail, raymarching.py:386-387)
+        const uint32_t row = n_alive * n_step + n;
+        if (row < M_padded) {
+            xyzs[(size_t)row * 3] = 0; xyzs[(size_t)row * 3 + 1] = 0; xyzs[(size_t)row * 3 + 2] = 0;
+            dirs[(size_t)row * 3] = 0; dirs[(size_t)row * 3 + 1] = 0; dirs[(size_t)row * 3 + 2] = 0;
+            deltas[(size_t)row * 2] = 0; deltas[(size_t)row * 2 + 1] = 0;
+        }
+    }
+    if (n >= n_alive) return;
+    const int index = rays_alive[n];
+    float t = rays_t[n];
+    const Ray r = load_ray(rays_o + (size_t)index * 3, rays_d + (size_t)index * 3);
+    const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H, grid);
+    float* px = xyzs + (size_t)n * n_step * 3;
+    float* pd = dirs + (size_t)n * n_step * 3;
+    float* pl = deltas + (size_t)n * n_step * 2;
+    const float far = fars[index];
+    if (perturb) {
+        Pcg32 rng; rng.seed((uint64_t)perturb);   // :1011
+        rng.advance(n);
+        t += p.dt_min * rng.next_float();
+    }
+    float last_t = t, x, y, z, dt;
+    uint32_t step = 0;
+    while (t < far && step < n_step) {
+        if (probe(r, p, t, x, y, z, dt)) {
+            px[0] = x; px[1] = y; px[2] = z;
+            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+            t += dt;
+            pl[0] = dt; pl[1] = t - last_t;
+            last_t = t;
+            px += 3; pd += 3; pl += 2; step++;
+        }
+    }
+    if (zero_fill) {
+        for (; step < n_step; step++) {
+            px[0] = 0; px[1] = 0; px[2] = 0; pd[0] = 0; pd[1] = 0; pd[2] = 0; pl[0] = 0; pl[1] = 0;
+            px += 3; pd += 3; pl += 2;
+        }
+    }
+}
+
+// raymarching.cu:1021-1104
+__global__ void __launch_bounds__(128) composite_rays_kernel(const uint32_t n_alive, const uint32_t n_step, const int* __restrict__ rays_alive,
+                                                             float* __restrict__ rays_t, const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                             const float* __restrict__ deltas, float* __restrict__ weights_sum, float* __restrict__ depth,
+                                                             float* __restrict__ image) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= n_alive) return;
+    const int index = rays_alive[n];
+    float t = rays_t[n];
+    sigmas += (size_t)n * n_step; rgbs += (size_t)n * n_step * 3; deltas += (size_t)n * n_step * 2;
+    float weight_sum = weights_sum[index], d = depth[index];
+    float r = image[(size_t)index * 3], g = image[(size_t)index * 3 + 1], b = image[(size_t)index * 3 + 2];
+    uint32_t step = 0;
+    while (step < n_step) {
+        if (deltas[0] == 0) break;
+        const float alpha = 1.0f - __expf(-sigmas[0] * deltas[0]);
+        const float T = 1 - weight_sum;
+        const float weight = alpha * T;
+        weight_sum += weight;
+        t += deltas[1];
+        d += weight * t;
+        r += weight * rgbs[0]; g += weight * rgbs[1]; b += weight * rgbs[2];
+        if (T < 1e-4) break;   // double literal on purpose (:1081)
+        sigmas++; rgbs += 3; deltas += 2; step++;
+    }
+    rays_t[n] = (step < n_step) ? -1.0f : t;
+    weights_sum[index] = weight_sum; depth[index] = d;
+    image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
+}
+
+// ordered stream compaction (raymarching.cu:1117-1134, atomics replaced by scans)
+constexpr int kCompactThreads = 256;
+constexpr int kCompactItems = 4;
+
+__global__ void __launch_bounds__(kCompactThreads) compact_rays_kernel(const uint32_t n_alive, int* __restrict__ rays_alive, const int* __restrict__ rays_alive_old,
+                                                                       float* __restrict__ rays_t, const float* __restrict__ rays_t_old, int* __restrict__ alive_counter,
+                                                                       ScanWS* ws) {
+    __shared__ uint32_t s_ticket;
+    __shared__ uint32_t s_warp[33];
+    __shared__ unsigned long long s_bcast;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&ws->ticket, 1u);
+    __syncthreads();
+    const uint32_t ticket = s_ticket;
+    const uint32_t first = (ticket * kCompactThreads + threadIdx.x) * kCompactItems;  // each thread owns 4 consecutive slots
+    int id[kCompactItems];
+    float tv[kCompactItems];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int i = 0; i < kCompactItems; i++) {
+        const uint32_t n = first + i;
+        tv[i] = -1.0f; id[i] = 0;
+        if (n < n_alive) { tv[i] = rays_t_old[n]; id[i] = rays_alive_old[n]; }
+        cnt += (tv[i] >= 0) ? 1u : 0u;
+    }
+    uint32_t block_total;
+    const uint32_t local = block_exclusive_scan(cnt, block_total, s_warp);
+    const unsigned long long base = (ticket == 0) ? (unsigned long long)(uint32_t)alive_counter[0] : 0ull;
+    const unsigned long long excl = chained_prefix(ws, ticket, block_total, base, &s_bcast);
+    const uint32_t nblocks = gridDim.x;
+    if (ticket == nblocks - 1 && threadIdx.x == 0) alive_counter[0] = (int)(uint32_t)(excl + block_total);
+    uint32_t dst = (uint32_t)excl + local;
+#pragma unroll
+    for (int i = 0; i < kCompactItems; i++) {
+        if (tv[i] >= 0) { rays_alive[dst] = id[i]; rays_t[dst] = tv[i]; dst++; }
+    }
+    scan_ws_release(ws, nblocks);
+}
+
+}  // namespace ntx
+
+using namespace ntx;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int ntx_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near, float* nears, float* fars,
+                                      ntx_stream_t stream) {
+    NTX_REQUIRE(rays_o && rays_d && aabb && nears && fars, NTX_ERR_INVALID_ARGUMENT, "near_far_from_aabb: null pointer");
+    if (N == 0) return NTX_OK;
+    near_far_kernel<<<ceil_div<uint32_t>(N, 128), 128, 0, ST(stream)>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
+    return check_launch("near_far_from_aabb");
+}
+
+extern "C" int ntx_polar_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords, ntx_stream_t stream) {
+    NTX_REQUIRE(rays_o && rays_d && coords, NTX_ERR_INVALID_ARGUMENT, "polar_from_ray: null pointer");
+    if (N == 0) return NTX_OK;
+    polar_kernel<<<ceil_div<uint32_t>(N, 128), 128, 0, ST(stream)>>>(rays_o, rays_d, radius, N, coords);
+    return check_launch("polar_from_ray");
+}
+
+extern "C" int ntx_morton3D(const int* coords, uint32_t N, int* indices, ntx_stream_t stream) {
+    NTX_REQUIRE(coords && indices, NTX_ERR_INVALID_ARGUMENT, "morton3D: null pointer");
+    if (N == 0) return NTX_OK;
+    morton3D_kernel<<<ceil_div<uint32_t>(N, 128), 128, 0, ST(stream)>>>(coords, N, indices);
+    return check_launch("morton3D");
+}
+
+extern "C" int ntx_morton3D_invert(const int* indices, uint32_t N, int* coords, ntx_stream_t stream) {
+    NTX_REQUIRE(coords && indices, NTX_ERR_INVALID_ARGUMENT, "morton3D_invert: null pointer");
+    if (N == 0) return NTX_OK;
+    morton3D_invert_kernel<<<ceil_div<uint32_t>(N, 128), 128, 0, ST(stream)>>>(indices, N, coords);
+    return check_launch("morton3D_invert");
+}
+
+extern "C" int ntx_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, ntx_stream_t stream) {
+    NTX_REQUIRE(grid && bitfield, NTX_ERR_INVALID_ARGUMENT, "packbits: null pointer");
+    if (N == 0) return NTX_OK;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(grid) & 15) == 0) && ((reinterpret_cast<uintptr_t>(bitfield) & 3) == 0);
+    const uint32_t vec_bytes = aligned ? (N / 4) * 4 : 0;
+    if (vec_bytes) packbits_kernel<<<min(ceil_div<uint32_t>(vec_bytes / 4, 256), 148u * 8u), 256, 0, ST(stream)>>>(grid, vec_bytes, density_thresh, bitfield);
+    if (vec_bytes < N) packbits_scalar_kernel<<<ceil_div<uint32_t>(N - vec_bytes, 128), 128, 0, ST(stream)>>>(grid, vec_bytes, N, density_thresh, bitfield);
+    return check_launch("packbits");
+}
+
+static size_t scan_ws_bytes(uint32_t nblocks) { return sizeof(uint32_t) * 2 + sizeof(unsigned long long) * (size_t)(nblocks ? nblocks : 1); }
+
+extern "C" size_t ntx_march_rays_train_workspace_bytes(uint32_t N) { return scan_ws_bytes(ceil_div<uint32_t>(N, kTrainThreads)); }
+
+extern "C" int ntx_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                                    uint32_t C, uint32_t H, uint32_t M, const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                                    float* rays_ts, int* rays, int* counter, uint32_t perturb, void* workspace, ntx_stream_t stream) {
+    NTX_REQUIRE(rays_o && rays_d && grid && nears && fars && xyzs && dirs && deltas && rays && counter, NTX_ERR_INVALID_ARGUMENT, "march_rays_train: null pointer");
+    NTX_REQUIRE(workspace, NTX_ERR_WORKSPACE, "march_rays_train: workspace of ntx_march_rays_train_workspace_bytes(N) bytes required");
+    NTX_REQUIRE(C >= 1 && C <= 16 && H >= 1 && H <= 1024 && max_steps >= 1, NTX_ERR_INVALID_ARGUMENT, "march_rays_train: bad C/H/max_steps");
+    if (N == 0) return NTX_OK;
+    march_rays_train_kernel<<<ceil_div<uint32_t>(N, kTrainThreads), kTrainThreads, 0, ST(stream)>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars,
+                                                                                                     xyzs, dirs, deltas, rays_ts, rays, counter, perturb,
+                                                                                                     static_cast<ScanWS*>(workspace));
+    return check_launch("march_rays_train");
+}
+
+extern "C" int ntx_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int* rays, uint32_t M, uint32_t N,
+                                                float* weights_sum, float* depth, float* image, ntx_stream_t stream) {
+    NTX_REQUIRE(sigmas && rgbs && deltas && rays && weights_sum && depth && image, NTX_ERR_INVALID_ARGUMENT, "composite_rays_train_forward: null pointer");
+    if (N == 0) return NTX_OK;
+    composite_train_fwd_kernel<<<ceil_div<uint32_t>(N, 128), 128, 0, ST(stream)>>>(sigmas, rgbs, deltas, rays, M, N, weights_sum, depth, image);
+    return check_launch("composite_rays_train_forward");
+}
+
+extern "C" int ntx_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image, const float* sigmas, const float* rgbs, const float* deltas,
+                                                 const int* rays, const float* weights_sum, const float* image, uint32_t M, uint32_t N, float* grad_sigmas,
+                                                 float* grad_rgbs, ntx_stream_t stream) {
+    NTX_REQUIRE(grad_weights_sum && grad_image && sigmas && rgbs && deltas && rays && weights_sum && image && grad_sigmas && grad_rgbs, NTX_ERR_INVALID_ARGUMENT,
+                "composite_rays_train_backward: null pointer");
+    if (N == 0) return NTX_OK;
+    composite_train_bwd_kernel<<<ceil_div<uint32_t>(N, 128), 128, 0, ST(stream)>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, M, N,
+                                                                                   grad_sigmas, grad_rgbs);
+    return check_launch("composite_rays_train_backward");
+}
+
+extern "C" int ntx_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, const float* rays_t, const float* rays_o, const float* rays_d, float bound,
+                              float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars, float* xyzs,
+                              float* dirs, float* deltas, uint32_t perturb, int zero_fill, uint32_t M_padded, ntx_stream_t stream) {
+    NTX_REQUIRE(rays_alive && rays_t && rays_o && rays_d && grid && nears && fars && xyzs && dirs && deltas, NTX_ERR_INVALID_ARGUMENT, "march_rays: null pointer");
+    NTX_REQUIRE(C >= 1 && C <= 16 && H >= 1 && H <= 1024 && max_steps >= 1, NTX_ERR_INVALID_ARGUMENT, "march_rays: bad C/H/max_steps");
+    NTX_REQUIRE(!zero_fill || M_padded >= n_alive * n_step, NTX_ERR_INVALID_ARGUMENT, "march_rays: M_padded smaller than n_alive*n_step");
+    uint32_t threads = n_alive;
+    if (zero_fill) threads = max(threads, M_padded - n_alive * n_step);
+    if (threads == 0) return NTX_OK;
+    march_rays_kernel<<<ceil_div<uint32_t>(threads, 128), 128, 0, ST(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid,
+                                                                               nears, fars, xyzs, dirs, deltas, perturb, zero_fill, M_padded);
+    return check_launch("march_rays");
+}
+
+extern "C" int ntx_composite_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, float* rays_t, const float* sigmas, const float* rgbs, const float* deltas,
+                                  float* weights_sum, float* depth, float* image, ntx_stream_t stream) {
+    NTX_REQUIRE(rays_alive && rays_t && sigmas && rgbs && deltas && weights_sum && depth && image, NTX_ERR_INVALID_ARGUMENT, "composite_rays: null pointer");
+    if (n_alive == 0) return NTX_OK;
+    composite_rays_kernel<<<ceil_div<uint32_t>(n_alive, 128), 128, 0, ST(stream)>>>(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image);
+    return check_launch("composite_rays");
+}
+
+extern "C" size_t ntx_compact_rays_workspace_bytes(uint32_t n_alive) { return scan_ws_bytes(ceil_div<uint32_t>(n_alive, kCompactThreads * kCompactItems)); }
+
+extern "C" int ntx_compact_rays(uint32_t n_alive, int* rays_alive, const int* rays_alive_old, float* rays_t, const float* rays_t_old, int* alive_counter,
+                                void* workspace, ntx_stream_t stream) {
+    NTX_REQUIRE(rays_alive && rays_alive_old && rays_t && rays_t_old && alive_counter, NTX_ERR_INVALID_ARGUMENT, "compact_rays: null pointer");
+    NTX_REQUIRE(workspace, NTX_ERR_WORKSPACE, "compact_rays: workspace of ntx_compact_rays_workspace_bytes(n_alive) bytes required");
+    if (n_alive == 0) return NTX_OK;
+    compact_rays_kernel<<<ceil_div<uint32_t>(n_alive, kCompactThreads * kCompactItems), kCompactThreads, 0, ST(stream)>>>(n_alive, rays_alive, rays_alive_old, rays_t,
+                                                                                                                         rays_t_old, alive_counter,
+                                                                                                                         static_cast<ScanWS*>(workspace));
+    return check_launch("compact_rays");
+}
