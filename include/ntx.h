@@ -70,9 +70,11 @@ int ntx_grid_debug_indices(const float* inputs, const int* offsets, uint32_t B, 
  * (ffmlp/src/ffmlp.h:8-14, ffmlp.cu:635,673,749,721,732).  All tensors fp16.
  *   inputs [B,input_dim]   weights flat [hidden*input_dim + (num_layers-1)*hidden*hidden + output_dim*hidden],
  *   each matrix row-major [out,in] (ffmlp.cu:632)   outputs [B,output_dim]   output_dim <= 16 is padded to 16
- *   by the caller (ffmlp.py:118); B must be a multiple of 128 (ffmlp.py:157).
+ *   by the caller (ffmlp.py:118).  The reference needs B % 128 == 0 (ffmlp.py:157 pads with zero rows); here any B works,
+ *   the kernel masks the ragged last 128-row tile.
  *   forward_buffer [num_layers,B,hidden] (training), backward_buffer likewise.  activation ids: ffmlp.cu:22-33.
- * hidden_dim in {16,32,64,128}; 256 and anything else -> NTX_ERR_UNSUPPORTED. */
+ * hidden_dim in {16,32,64,128,256} (ffmlp.cu:652-659), as long as all weight matrices + one 128-row activation tile fit
+ * the SM's 227 KB of shared memory; anything else -> NTX_ERR_UNSUPPORTED. */
 int ntx_ffmlp_forward(const void* inputs, const void* weights, uint32_t B, uint32_t input_dim, uint32_t output_dim,
                       uint32_t hidden_dim, uint32_t num_layers, uint32_t activation, uint32_t output_activation,
                       void* forward_buffer, void* outputs, ntx_stream_t stream);
