@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — ray-samples/sec of the per-ray-sample hot path (march -> hash-grid -> fused MLPs -> composite) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one 1024x1024 frame of BASELINE config 3 (random-weight network_ff field, ball occupancy, bound 1, dt_gamma 0,
+max_steps 1024) rendered through the libntx C ABI; with N > 1 the frame's rays are sharded over the ranks in interleaved
+tiles and the result is all-gathered (config 4, strong scaling).  `value` = non-sentinel samples of the frame / device
+time (CUDA events, max over ranks, inputs resident in HBM); `e2e` = the same with rays coming from pinned host memory and
+the image read back every step.  `roofline` is for the dominant kernel (the fused field kernel: hash-grid gather + both
+MLPs), measured live with CUDA events around every launch of one extra frame.  `cfg2` reports BASELINE config 2 (2^20
+random and ray-coherent samples through the fused field kernel and through the stand-alone grid encoder).
+`cpu_baseline` / `--impl reference`: the reference has no CPU implementation of this path, so the CPU arm is
+the oracle port (oracle/ntx_oracle.c, OpenMP over all host cores) rendering a strided sub-sample of the same frame.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ray-samples/sec (encoder+MLP+composite)"
+UNIT = "samples/s"
+IMG = 1024
+FIELD_BYTES_PER_SAMPLE = 12 + 12 + 4 + 512 + 4 + 12   # xyz, dir, delta | 16 levels x 8 corners x 2 x fp16 | sigma, rgb  
+GRID_BYTES_PER_SAMPLE = 12 + 512 + 64                 # stand-alone encoder, fp16 table
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi SM clocks + throttle reasons while the timed region runs"""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene(device, seed=0):
+    from nerf_texture_b200 import render, scene
+    field = render.NGPField.random(device, seed=seed)
+    rays_o, rays_d = scene.pinhole_rays(IMG, IMG, device)
+    bits = scene.ball_bitfield(1, 128, 1.0, device)
+    return field, rays_o, rays_d, bits
+
+
+def cpu_render_sample(stride=5, steps=1, warmup=0):
+    """oracle (CPU) render of every `stride`-th pixel row/column of the same frame; returns samples/s and a description"""
+    import numpy as np
+    from oracle import oracle as O
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _util import ball_density_grid, pinhole_rays
+    o, d = pinhole_rays(IMG, IMG)
+    sel = np.zeros((IMG, IMG), bool)
+    sel[::stride, ::stride] = True
+    o, d = np.ascontiguousarray(o[sel.ravel()]), np.ascontiguousarray(d[sel.ravel()])
+    bits = O.packbits(ball_density_grid(1, 128, 1.0), 0.5)
+    offs, pls = O.grid_offsets(3, 16, 2, base_resolution=16, log2_hashmap_size=19, desired_resolution=2048, align_corners=True)
+    rng = np.random.default_rng(1)
+    emb = (rng.random((int(offs[-1]), 2), dtype=np.float32) * 2 - 1).astype(np.float16)
+    ws = ((rng.random(64 * (32 + 64 + 16), dtype=np.float32) * 2 - 1) * np.sqrt(3 / 64)).astype(np.float16)
+    wc = ((rng.random(64 * (32 + 128 + 16), dtype=np.float32) * 2 - 1) * np.sqrt(3 / 64)).astype(np.float16)
+    times, ns = [], 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, _, _, ns, _ = O.render_rays(o, d, bits, 1, 128, 1.0, emb, offs, pls, 16, ws, wc)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return ns / dt, dt, ns, O.num_threads(), "oracle port (oracle/ntx_oracle.c, OpenMP): every %dth row/column of the 1024x1024 frame = %d rays, %d samples per step" % (stride, o.shape[0], ns)
+
+
+def reference_arm(args):
+    """`--impl reference`: the CPU port of the reference path on the host cores (the reference itself is CUDA-only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, dt, ns, cores, sample = cpu_render_sample(stride=6, steps=max(1, args.steps), warmup=min(1, args.warmup))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": "render_1024x1024_network_ff_random_weights (BASELINE config 3), CPU sub-sample", "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ntx", choices=["ntx", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cfg2 / roofline side measurements")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from nerf_texture_b200 import _lib as L
+    from nerf_texture_b200 import render
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    W, K = max(args.warmup, 3), args.steps
+    L.lib()
+    assert L.lib().ntx_device_ok() == 1, "libntx needs a CC 10.x device"
+
+    field, rays_o, rays_d, bits = build_scene(device)
+    N = rays_o.shape[0]
+    if world > 1:
+        idx = render.shard_indices(N, world, rank).to(device)
+        my_o, my_d = rays_o[idx].contiguous(), rays_d[idx].contiguous()
+    else:
+        my_o, my_d = rays_o, rays_d
+
+    def step_device():
+        out = render.render_rays(field, my_o, my_d, bits, 1, 128)     # this rank's (resident) shard of the frame
+        return render.gather_frame(out, N) if world > 1 else out      # + the tile all-gather (config 4)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # samples per frame (untimed, counted once: the scene is deterministic)
+    cnt = render.render_rays(field, my_o, my_d, bits, 1, 128, count_samples=True)
+    n_local = torch.tensor([cnt["n_samples"]], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(n_local)
+    samples_per_frame = int(n_local.item())
+    iterations = cnt["iterations"]
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)   # > 126 MB L2
+
+    def timed(fn, steps):
+        evs = []
+        barrier()
+        for _ in range(steps):
+            flush.zero_()                      # L2 flush between timed iterations (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            evs.append((e0, e1))
+        barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps         # ms per step, max over ranks
+
+    for _ in range(W):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = L.launches
+    ms = timed(step_device, K)
+    launches = (L.launches - l0) // K
+    clocks = sampler.stop() if rank == 0 else None
+    value = samples_per_frame / (ms * 1e-3)
+
+    # ---- end to end: rays from pinned host memory each step, image + depth read back each step --------------------
+    h_o, h_d = my_o.cpu().pin_memory(), my_d.cpu().pin_memory()
+    d_o, d_d = torch.empty_like(my_o), torch.empty_like(my_d)
+    h_img = torch.empty(N, 3, dtype=torch.float32).pin_memory()
+    h_dep = torch.empty(N, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        d_o.copy_(h_o, non_blocking=True); d_d.copy_(h_d, non_blocking=True)
+        out = render.render_rays(field, d_o, d_d, bits, 1, 128)       # each rank uploads and renders its own shard
+        if world > 1:
+            out = render.gather_frame(out, N)
+        if rank == 0:
+            h_img.copy_(out["image"], non_blocking=True); h_dep.copy_(out["depth"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, max(3, K // 2))
+    e2e = {"value": samples_per_frame / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": int(h_o.numel() * 4 * 2 * world), "d2h_bytes_per_step": int(N * 16)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": "render_1024x1024_network_ff_random_weights (BASELINE config 3%s)" % ("; rays sharded in interleaved 1024-ray tiles + one NCCL all_gather, config 4" if world > 1 else ""),
+                   "field": "hashgrid L=16 T=2^19 F=2 fp16 -> FFMLP(32,16,64,2) -> SH4 -> FFMLP(32,3,64,3)", "rays": N, "samples_per_frame": samples_per_frame,
+                   "loop_iterations": iterations, "max_steps": 1024, "dt_gamma": 0, "occupancy": "ball r=0.5, H=128, 1 cascade",
+                   "l2": "flushed between timed steps (256 MiB memset)", "parallelism": "ray-sharded x%d" % world},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+    }
+
+    if rank == 0 and not args.no_extras:
+        peaks, peak_src = measured_peaks()
+        # ---- roofline of the dominant kernel: every field launch of one frame bracketed by CUDA events -----------------
+        prof = []
+        render.render_rays(field, my_o, my_d, bits, 1, 128, profile=prof)
+        render.render_rays(field, my_o, my_d, bits, 1, 128, profile=(prof := []))
+        torch.cuda.synchronize()
+        kt = sum(a.elapsed_time(b) for a, b, _, _ in prof) * 1e-3
+        live = sum(int(c.item()) for _, _, c, _ in prof)
+        rows = sum(m for _, _, _, m in prof)
+        achieved = live * FIELD_BYTES_PER_SAMPLE / kt / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": "ngp_field_kernel (hash-grid gather + sigma MLP + SH + colour MLP)", "achieved": achieved,
+                            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                            "algorithmic_bytes_per_sample": FIELD_BYTES_PER_SAMPLE, "launches": len(prof), "avg_launch_us": kt / max(len(prof), 1) * 1e6,
+                            "live_samples": live, "rows": rows, "kernel_share_of_step": kt * 1e3 / ms,
+                            "msamples_per_s_in_kernel": live / kt / 1e6,
+                            "tensor_note": "36864 FLOP/sample on tcgen05: %.1f TFLOP/s achieved inside the kernel" % (live * 36864 / kt / 1e12)}
+        # ---- BASELINE config 2: 2^20 samples through the fused field kernel and the stand-alone encoder ------------
+        line["cfg2"] = bench_cfg2(torch, L, field, device, peaks)
+        if not args.no_cpu_baseline and world == 1:
+            v, dt, ns, cores, sample = cpu_render_sample(stride=5)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "seconds": dt}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_cfg2(torch, L, field, device, peaks):
+    import math
+    B = 1 << 20
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x_rand = (torch.rand(B, 3, generator=g) * 2 - 1).to(device)
+    d = torch.randn(B, 3, generator=g)
+    d = (d / d.norm(dim=1, keepdim=True)).to(device)
+    # ray-coherent variant: 4096 rays x 256 steps of dt_min through the unit cube
+    o = (torch.rand(4096, 1, 3, generator=g) * 0.6 - 0.3)
+    dd = torch.randn(4096, 1, 3, generator=g); dd = dd / dd.norm(dim=-1, keepdim=True)
+    t = (torch.arange(256).float() * (2 * math.sqrt(3) / 1024)).view(1, 256, 1)
+    x_coh = (o + dd * t).clamp(-1, 1).reshape(-1, 3).contiguous().to(device)
+    d_coh = dd.expand(4096, 256, 3).reshape(-1, 3).contiguous().to(device)
+    sig = torch.empty(B, device=device); rgb = torch.empty(B, 3, device=device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    out = {}
+
+    def time_it(fn, iters=20):
+        for _ in range(3):
+            fn()
+        evs = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) for a, b in evs)
+        return ts[len(ts) // 2] * 1e-3
+
+    for name, xs, ds in (("random", x_rand, d), ("coherent", x_coh, d_coh)):
+        t_f = time_it(lambda: field(xs, ds, out_sigmas=sig, out_rgbs=rgb))
+        x01 = ((xs + 1) / 2).contiguous()
+        feat = torch.empty(B, 32, dtype=torch.half, device=device)
+        t_g = time_it(lambda: L.call("ntx_grid_encode_forward", L.ptr(x01), L.ptr(field.table), L.ptr(field.offsets), L.ptr(feat), B, 3, 2, 16, field.S,
+                                     field.H, 0, None, 0, 1, L.F16, L.LAYOUT_BLC, L.stream()))
+        out[name] = {"fused_field_msamples_per_s": B / t_f / 1e6, "fused_field_us": t_f * 1e6,
+                     "fused_field_gbs": B * FIELD_BYTES_PER_SAMPLE / t_f / 1e9, "fused_field_frac_hbm": B * FIELD_BYTES_PER_SAMPLE / t_f / 1e9 / peaks["hbm_gbs"],
+                     "fused_field_tflops": B * 36864 / t_f / 1e12,
+                     "grid_encode_msamples_per_s": B / t_g / 1e6, "grid_encode_us": t_g * 1e6, "grid_encode_gbs": B * GRID_BYTES_PER_SAMPLE / t_g / 1e9,
+                     "grid_encode_frac_hbm": B * GRID_BYTES_PER_SAMPLE / t_g / 1e9 / peaks["hbm_gbs"]}
+    feat = torch.randn(B, 32, device=device).half()
+    h = torch.empty(B, 16, dtype=torch.half, device=device)
+    t_m = time_it(lambda: L.call("ntx_ffmlp_inference", L.ptr(feat), L.ptr(field.w_sigma), B, 32, 16, 64, 2, 0, 6, None, L.ptr(h), L.stream()))
+    out["ffmlp_32_64_64_16"] = {"us": t_m * 1e6, "tflops": B * 14336 / t_m / 1e12, "frac_tensor_peak": B * 14336 / t_m / 1e12 / peaks["bf16_tflops"],
+                                "io_gbs": B * 96 / t_m / 1e9, "io_frac_hbm": B * 96 / t_m / 1e9 / peaks["hbm_gbs"]}
+    out["note"] = "2^20 samples, fp16 table 23.3 MiB (L2-resident), L2 flushed before every timed launch, median of 20"
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -77,8 +77,15 @@ def check(rc):
         raise RuntimeError(lib().ntx_last_error().decode() or "libntx error %d" % rc)
 
 
+launches = 0  # number of libntx kernel-launching calls made by this process (bench.py reports the delta as gpu_launches)
+_NO_LAUNCH = {"ntx_allocate_splitk", "ntx_free_splitk"}
+
+
 def call(name, *args):
+    global launches
     check(getattr(lib(), name)(*args))
+    if name not in _NO_LAUNCH:
+        launches += 1
 
 
 def ptr(t):

@@ -1,0 +1,208 @@
+"""Inference rendering on libntx: the loop of nerf/renderer.py::run_cuda (reference :446-489) with the fused field kernel.
+
+`NGPField` packs the parameters of the network_ff topology (hash-grid + two FFMLPs) once — fp16 table, fp16 weights —
+and evaluates sigma/rgb for a batch of samples with ONE kernel launch (ntx_ngp_field_forward).
+`render_rays` is the reference's march -> field -> composite -> compact loop over the same C ABI the drop-in
+`raymarching` package uses; buffers are allocated once per call, the only device->host traffic is the 4-byte alive
+counter per iteration (the reference has the same sync, renderer.py:469).
+`render_image_sharded` splits the rays of one frame over the ranks of a torch.distributed group in interleaved tiles and
+all-gathers the packed result (rgb, depth, alpha = 20 B/ray) — the only collective on the path.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+class NGPField:
+    """hash-grid (D=3, C=2) -> FFMLP(2L,16,64,2) -> exp | SH4 ++ geo_feat -> FFMLP(32,3,64,3) -> sigmoid  (nerf/network_ff.py)"""
+
+    def __init__(self, embeddings, offsets, per_level_scale, base_resolution, w_sigma, w_color, bound=1.0, align_corners=True,
+                 density_scale=1.0):
+        dev = embeddings.device
+        self.table = embeddings.detach().to(torch.half).contiguous()           # [n_entries, 2] fp16, cast ONCE
+        self.offsets = offsets.detach().to(device=dev, dtype=torch.int32).contiguous()
+        self.num_levels = int(self.offsets.shape[0] - 1)
+        self.S = float(np.log2(per_level_scale))
+        self.H = int(base_resolution)
+        self.align_corners = bool(align_corners)
+        self.w_sigma = w_sigma.detach().to(device=dev, dtype=torch.half).contiguous()
+        self.w_color = w_color.detach().to(device=dev, dtype=torch.half).contiguous()
+        self.bound = float(bound)
+        self.density_scale = float(density_scale)
+        nfeat = 2 * self.num_levels
+        assert self.table.shape[1] == 2, "fused field needs level_dim == 2"
+        assert self.w_sigma.numel() == 64 * (nfeat + 64 + 16), "sigma net must be FFMLP(2L, 16, 64, num_layers=2)"
+        assert self.w_color.numel() == 64 * (32 + 2 * 64 + 16), "colour net must be FFMLP(32, 3, 64, num_layers=3)"
+
+    @classmethod
+    def from_modules(cls, encoder, sigma_net, color_net, bound=1.0, density_scale=1.0):
+        """encoder: gridencoder.GridEncoder, sigma_net / color_net: ffmlp.FFMLP (as built by nerf/network_ff.py:29-49)"""
+        return cls(encoder.embeddings, encoder.offsets, encoder.per_level_scale, encoder.base_resolution, sigma_net.weights, color_net.weights,
+                   bound=bound, align_corners=encoder.align_corners, density_scale=density_scale)
+
+    @classmethod
+    def random(cls, device, num_levels=16, base_resolution=16, log2_hashmap_size=19, desired_resolution=2048, bound=1.0, seed=0,
+               table_std=1.0, align_corners=True):
+        """random-weight field of BASELINE config 2/3 (table U(-1,1) seed `seed`+1, MLP weights U(+-sqrt(3/64)) like ffmlp.py:141-144)"""
+        pls = float(np.exp2(np.log2(desired_resolution * bound / base_resolution) / (num_levels - 1)))
+        offs, off = [], 0
+        for i in range(num_levels):
+            res = int(np.ceil(base_resolution * pls ** i))
+            n = min(2 ** log2_hashmap_size, (res if align_corners else res + 1) ** 3)
+            n = int(np.ceil(n / 8) * 8)
+            offs.append(off)
+            off += n
+        offs.append(off)
+        g = torch.Generator(device="cpu").manual_seed(seed + 1)
+        table = (torch.rand(off, 2, generator=g) * 2 - 1) * table_std
+        g2 = torch.Generator(device="cpu").manual_seed(42)
+        std = math.sqrt(3 / 64)
+        ws = (torch.rand(64 * (2 * num_levels + 64 + 16), generator=g2) * 2 - 1) * std
+        wc = (torch.rand(64 * (32 + 128 + 16), generator=g2) * 2 - 1) * std
+        return cls(table.to(device), torch.tensor(offs, dtype=torch.int32, device=device), pls, base_resolution, ws.to(device), wc.to(device),
+                   bound=bound, align_corners=align_corners)
+
+    def __call__(self, xyzs, dirs, deltas=None, out_sigmas=None, out_rgbs=None, M=None):
+        M = xyzs.shape[0] if M is None else M
+        sig = out_sigmas if out_sigmas is not None else torch.empty(M, dtype=torch.float32, device=xyzs.device)
+        rgb = out_rgbs if out_rgbs is not None else torch.empty(M, 3, dtype=torch.float32, device=xyzs.device)
+        L.call("ntx_ngp_field_forward", L.ptr(xyzs), L.ptr(dirs), None if deltas is None else L.ptr(deltas), int(M), self.bound, L.ptr(self.table),
+               L.ptr(self.offsets), self.num_levels, self.S, self.H, int(self.align_corners), L.ptr(self.w_sigma), L.ptr(self.w_color),
+               self.density_scale, L.ptr(sig), L.ptr(rgb), L.stream())
+        return sig, rgb
+
+
+def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aabb=None, min_near=0.2, dt_gamma=0.0, max_steps=1024, bg_color=1.0,
+                perturb=0, count_samples=False, profile=None):
+    """Inference branch of NeRFRenderer.run_cuda (renderer.py:436-489).  rays_o/d [N,3] fp32 CUDA.
+    Returns dict(image [N,3], depth [N], weights_sum [N], iterations, n_samples (if count_samples)).
+    profile: optional list; gets one (start_event, stop_event, live_sample_count_tensor) per field-kernel launch."""
+    dev = rays_o.device
+    rays_o = rays_o.contiguous().view(-1, 3).float()
+    rays_d = rays_d.contiguous().view(-1, 3).float()
+    N = rays_o.shape[0]
+    bound = field.bound
+    if aabb is None:
+        aabb = torch.tensor([-bound, -bound, -bound, bound, bound, bound], dtype=torch.float32, device=dev)
+    st = L.stream()
+    nears = torch.empty(N, dtype=torch.float32, device=dev)
+    fars = torch.empty(N, dtype=torch.float32, device=dev)
+    L.call("ntx_near_far_from_aabb", L.ptr(rays_o), L.ptr(rays_d), L.ptr(aabb), N, float(min_near), L.ptr(nears), L.ptr(fars), st)
+
+    weights_sum = torch.zeros(N, dtype=torch.float32, device=dev)
+    depth = torch.zeros(N, dtype=torch.float32, device=dev)
+    image = torch.zeros(N, 3, dtype=torch.float32, device=dev)
+    rays_alive = torch.empty(2, N, dtype=torch.int32, device=dev)
+    rays_t = torch.empty(2, N, dtype=torch.float32, device=dev)
+    torch.arange(N, out=rays_alive[0])
+    rays_t[0].copy_(nears)
+    alive_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+    Mmax = N + 128                      # n_alive * n_step <= N, padded to 128 like the reference (align=128)
+    xyzs = torch.empty(Mmax, 3, dtype=torch.float32, device=dev)
+    dirs = torch.empty(Mmax, 3, dtype=torch.float32, device=dev)
+    deltas = torch.empty(Mmax, 2, dtype=torch.float32, device=dev)
+    sigmas = torch.empty(Mmax, dtype=torch.float32, device=dev)
+    rgbs = torch.empty(Mmax, 3, dtype=torch.float32, device=dev)
+    ws = L.workspace("compact", L.lib().ntx_compact_rays_workspace_bytes(N), dev)
+    n_samples = torch.zeros(1, dtype=torch.int64, device=dev) if count_samples else None
+
+    n_alive, step, i = N, 0, 0
+    while step < max_steps:
+        cur, old = i % 2, (i + 1) % 2
+        if step > 0:
+            alive_counter.zero_()
+            L.call("ntx_compact_rays", n_alive, L.ptr(rays_alive[cur]), L.ptr(rays_alive[old]), L.ptr(rays_t[cur]), L.ptr(rays_t[old]),
+                   L.ptr(alive_counter), L.ptr(ws), st)
+            n_alive = int(alive_counter.item())     # the loop's one D2H sync (renderer.py:469)
+        if n_alive <= 0:
+            break
+        n_step = max(min(N // n_alive, 8), 1)
+        M = n_alive * n_step
+        M += 128 - (M % 128)
+        L.call("ntx_march_rays", n_alive, n_step, L.ptr(rays_alive[cur]), L.ptr(rays_t[cur]), L.ptr(rays_o), L.ptr(rays_d), bound, float(dt_gamma),
+               int(max_steps), int(cascade), int(grid_size), L.ptr(density_bitfield), L.ptr(nears), L.ptr(fars), L.ptr(xyzs), L.ptr(dirs), L.ptr(deltas),
+               int(perturb), 1, M, st)
+        if profile is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            field(xyzs, dirs, deltas, out_sigmas=sigmas, out_rgbs=rgbs, M=M)
+            e1.record()
+            profile.append((e0, e1, (deltas[:M, 0] > 0).sum(), M))
+        else:
+            field(xyzs, dirs, deltas, out_sigmas=sigmas, out_rgbs=rgbs, M=M)
+        if count_samples:
+            n_samples += (deltas[:M, 0] > 0).sum()
+        L.call("ntx_composite_rays", n_alive, n_step, L.ptr(rays_alive[cur]), L.ptr(rays_t[cur]), L.ptr(sigmas), L.ptr(rgbs), L.ptr(deltas),
+               L.ptr(weights_sum), L.ptr(depth), L.ptr(image), st)
+        step += n_step
+        i += 1
+    image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+    out = dict(image=image, depth=depth, weights_sum=weights_sum, iterations=i)
+    if count_samples:
+        out["n_samples"] = int(n_samples.item())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ multi-GPU
+def shard_indices(N, world_size, rank, tile=1024):
+    """Interleaved ray tiles: tile k goes to rank k % world_size.  Per-ray cost varies >100x between rays that miss and rays
+    that cross the object; contiguous blocks would put the object on a few ranks only."""
+    ntiles = (N + tile - 1) // tile
+    mine = torch.arange(rank, ntiles, world_size)
+    idx = (mine[:, None] * tile + torch.arange(tile)[None, :]).reshape(-1)
+    return idx[idx < N]
+
+
+_shard_cache = {}
+
+
+def _shard_plan(N, world, tile, device):
+    """per-rank ray indices (on `device`), rows of the padded per-rank block, and the inverse permutation of the gathered rows"""
+    key = (N, world, tile, str(device))
+    plan = _shard_cache.get(key)
+    if plan is None:
+        idxs = [shard_indices(N, world, r, tile) for r in range(world)]
+        n_max = max(i.numel() for i in idxs)
+        # gathered row (r * n_max + j) holds ray idxs[r][j]  ->  dest[ray] = gathered row
+        src = torch.cat([r * n_max + torch.arange(i.numel()) for r, i in enumerate(idxs)])
+        inv = torch.empty(N, dtype=torch.long)
+        inv[torch.cat(idxs)] = src
+        plan = ([i.to(device) for i in idxs], n_max, inv.to(device))
+        _shard_cache[key] = plan
+    return plan
+
+
+def gather_frame(out, N, group=None, tile=1024):
+    """ONE all_gather of the packed per-rank result (rgb, depth, alpha = 20 B/ray) + un-permute to image order."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = out["image"].device
+    idxs, n_max, inv = _shard_plan(N, world, tile, dev)
+    n_local = idxs[rank].numel()
+    packed = torch.empty(n_max, 5, dtype=torch.float32, device=dev)
+    packed[:n_local, 0:3] = out["image"]
+    packed[:n_local, 3] = out["depth"]
+    packed[:n_local, 4] = out["weights_sum"]
+    gathered = torch.empty(world * n_max, 5, dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(gathered, packed, group=group)        # the path's only collective (NCCL over NVLink)
+    full = gathered[inv]
+    res = dict(image=full[:, 0:3], depth=full[:, 3], weights_sum=full[:, 4], iterations=out["iterations"])
+    if "n_samples" in out:
+        res["n_samples"] = out["n_samples"]
+    return res
+
+
+def render_image_sharded(field, rays_o, rays_d, density_bitfield, cascade, grid_size, group=None, tile=1024, **kw):
+    """Each rank renders its interleaved tiles of the frame; ONE all_gather of the packed (rgb, depth, alpha) rows follows.
+    rays_o/rays_d: the full frame's rays on every rank ([N,3], e.g. generated on-device from the pose)."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, **kw)
+    N = rays_o.shape[0]
+    idxs, _, _ = _shard_plan(N, dist.get_world_size(group), tile, rays_o.device)
+    idx = idxs[dist.get_rank(group)]
+    out = render_rays(field, rays_o[idx], rays_d[idx], density_bitfield, cascade, grid_size, **kw)
+    return gather_frame(out, N, group, tile)

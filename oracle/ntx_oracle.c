@@ -581,7 +581,7 @@ void orc_march_rays_train(const float* rays_o, const float* rays_d, const uint8_
         orc_ray_ctx c; orc_ray_ctx_init(&c, rays_o + n * 3, rays_d + n * 3, bound, dt_gamma, max_steps, C, H, grid);
         const float far = fars[n];
         float t0 = nears[n];
-        if (perturb) { orc_pcg32 r; orc_pcg_seed(&r, 42, 1); orc_pcg_advance(&r, (int64_t)n); t0 += c.dt_min * orc_pcg_next_float(&r); }
+        if (perturb) { orc_pcg32 r; orc_pcg_seed(&r, 42, 1); orc_pcg_advance(&r, (int64_t)n); t0 = fmaf(c.dt_min, orc_pcg_next_float(&r), t0); /* contracted on the GPU */ }
         float t = t0, x, y, z, dt; uint32_t num_steps = 0;
         while (t < far && num_steps < max_steps) { if (orc_probe(&c, &t, &x, &y, &z, &dt)) { num_steps++; t += dt; } }
         const uint32_t point_index = (uint32_t)counter[0]; counter[0] += (int)num_steps;
@@ -670,7 +670,7 @@ void orc_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, co
         orc_ray_ctx c; orc_ray_ctx_init(&c, rays_o + (size_t)index * 3, rays_d + (size_t)index * 3, bound, dt_gamma, max_steps, C, H, grid);
         const float far = fars[index];
         float* px = xyzs + (size_t)n * n_step * 3; float* pd = dirs + (size_t)n * n_step * 3; float* pl = deltas + (size_t)n * n_step * 2;
-        if (perturb) { orc_pcg32 r; orc_pcg_seed(&r, (uint64_t)perturb, 1); orc_pcg_advance(&r, (int64_t)n); t += c.dt_min * orc_pcg_next_float(&r); }
+        if (perturb) { orc_pcg32 r; orc_pcg_seed(&r, (uint64_t)perturb, 1); orc_pcg_advance(&r, (int64_t)n); t = fmaf(c.dt_min, orc_pcg_next_float(&r), t); /* contracted on the GPU */ }
         float last_t = t, x, y, z, dt; uint32_t step = 0;
         while (t < far && step < n_step) {
             if (orc_probe(&c, &t, &x, &y, &z, &dt)) {

@@ -340,3 +340,40 @@ def ngp_field(xyz, dirs, bound, embeddings_f16, offsets, per_level_scale, base_r
     hc = ffmlp_forward(cin, w_color, cin.shape[1], 16, 64, 3, acc_mode=acc_mode)[:, :3]
     rgb = (1.0 / (1.0 + np.exp(-hc.astype(np.float32)))).astype(np.float16).astype(np.float32)
     return sigma, rgb
+
+
+# ------------------------------------------------------------------------------------------------ whole-frame loop
+def render_rays(rays_o, rays_d, bitfield, cascade, grid_size, bound, embeddings_f16, offsets, per_level_scale, base_resolution, w_sigma,
+                w_color, align_corners=True, min_near=0.2, dt_gamma=0.0, max_steps=1024, bg_color=1.0, perturb=0, density_scale=1.0,
+                level_scales=None):
+    """CPU restatement of the inference branch of NeRFRenderer.run_cuda (nerf/renderer.py:436-489) over the oracle ops.
+    Returns image [N,3], depth [N], weights_sum [N], number of non-sentinel samples, iterations."""
+    o = _c(rays_o, np.float32).reshape(-1, 3)
+    d = _c(rays_d, np.float32).reshape(-1, 3)
+    N = o.shape[0]
+    aabb = np.array([-bound] * 3 + [bound] * 3, np.float32)
+    nears, fars = near_far_from_aabb(o, d, aabb, min_near)
+    weights_sum, depth, image = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros((N, 3), np.float32)
+    alive, t = np.arange(N, dtype=np.int32), nears.copy()
+    n_alive, step, it, n_samples = N, 0, 0, 0
+    while step < max_steps:
+        if step > 0:
+            alive, t, n_alive = compact_rays(n_alive, alive, t)
+        if n_alive <= 0:
+            break
+        n_step = max(min(N // n_alive, 8), 1)
+        xyzs, dirs, deltas = march_rays(n_alive, n_step, alive, t, o, d, bound, bitfield, cascade, grid_size, nears, fars, align=128,
+                                        perturb=perturb, dt_gamma=dt_gamma, max_steps=max_steps)
+        live = deltas[:, 0] > 0
+        n_samples += int(live.sum())
+        sig, rgb = ngp_field(xyzs, dirs, bound, embeddings_f16, offsets, per_level_scale, base_resolution, w_sigma, w_color,
+                             align_corners=align_corners, level_scales=level_scales)
+        sig = (np.float32(density_scale) * sig).astype(np.float32)
+        tt = np.ascontiguousarray(t[:n_alive])
+        composite_rays(n_alive, n_step, alive, tt, sig, rgb, deltas, weights_sum, depth, image)
+        t = tt
+        alive = alive[:n_alive]
+        step += n_step
+        it += 1
+    image = image + (1 - weights_sum)[:, None] * np.float32(bg_color)
+    return image, depth, weights_sum, n_samples, it
