@@ -1,6 +1,7 @@
 // api.cu — error reporting and library-level entry points of libntx.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace ntx {
@@ -10,6 +11,17 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+const Tunables& tunables() {
+    static Tunables t = [] {
+        Tunables v;
+        const char* e;
+        v.l1_keep_bytes = (e = getenv("NTX_L1_KEEP_BYTES")) ? (uint32_t)strtoul(e, nullptr, 0) : 0xffffffffu;
+        v.field_ctas = (e = getenv("NTX_FIELD_CTAS")) ? atoi(e) : 0;
+        v.pair_ctas = (e = getenv("NTX_PAIR_CTAS")) ? atoi(e) : 0;
+        return v;
+    }();
+    return t;
 }
 }  // namespace ntx
 

@@ -22,6 +22,14 @@ constexpr int kNumSMs = 148;  // B200
 
 void set_error(const char* fmt, ...);
 
+// run-time tuning knobs (environment variables, read once): experiments without rebuilding
+struct Tunables {
+    uint32_t l1_keep_bytes;  // NTX_L1_KEEP_BYTES: grid levels up to this size use L1-allocating loads, larger ones L1::no_allocate
+    int field_ctas;          // NTX_FIELD_CTAS: resident CTAs per SM of the fused field kernel (0 = as many as fit)
+    int pair_ctas;           // NTX_PAIR_CTAS: same for the stand-alone pair gather kernel
+};
+const Tunables& tunables();
+
 inline int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -41,6 +49,32 @@ inline int check_launch(const char* what) {
 
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+// Resident CTAs per SM of a kernel, from registers / shared memory / threads / tensor-memory columns.
+// (cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1 for kernels containing tcgen05.alloc — measured on B200 — although
+// several such CTAs do co-reside as long as their TMEM columns sum to <= 512, so persistent grids are sized with this instead.)
+inline int resident_ctas_per_sm(const void* func, int threads, size_t dyn_smem, int tmem_cols) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, func) != cudaSuccess) { cudaGetLastError(); return 1; }
+    int dev = 0, regs_sm = 65536, smem_sm = 233472, thr_sm = 2048;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&thr_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+    const int regs = ((fa.numRegs + 7) / 8) * 8;  // allocation granularity
+    int n = regs_sm / std::max(1, regs * threads);
+    n = std::min(n, (int)(smem_sm / (dyn_smem + fa.sharedSizeBytes + 1024)));  // 1 KB reserved per CTA
+    n = std::min(n, thr_sm / threads);
+    if (tmem_cols > 0) n = std::min(n, 512 / tmem_cols);
+    n = std::min(n, 32);
+    return std::max(n, 1);
+}
+inline int device_sm_count() {
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
 
 // ---- cache-hinted accesses ---------------------------------------------------------------------------
 // streaming (read-once) 128-bit load that does not pollute L1

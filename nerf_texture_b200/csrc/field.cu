@@ -7,25 +7,34 @@
 //
 // The reference runs this as 4 extension calls + ~10 torch glue kernels with every intermediate (features 64 B, padded
 // copies, geo_feat, SH 64 B, concatenated colour input 64 B ...) making a round trip through HBM.
-// Here a CTA owns 128 samples: features are produced straight into the shared-memory A tile of the first UMMA, hidden
-// activations ping through TMEM <-> shared memory, geo_feat goes from the sigma net's TMEM accumulator into the colour
-// net's A tile, and only xyz/dir (24 B) come in and sigma/rgb (16 B) go out per sample.
-// Several CTAs are resident per SM so one CTA's MMA/epilogue chain overlaps the others' gathers.
+// Here a CTA owns 128-sample tiles and is warp-specialised:
+//   * 8 producer warps (256 threads = 128 lane pairs) gather the features of a tile straight into the shared-memory A
+//     operand of the first UMMA and evaluate SH into the colour net's A operand, then move on to the next tile;
+//   * 4 consumer warps (one per TMEM lane quarter) run the two MLPs of the previous tile: one thread issues the
+//     tcgen05.mma of a layer, the warps pull the accumulator out of TMEM, apply ReLU, round to fp16 and write the next
+//     layer's A operand; geo_feat goes from the sigma net's accumulator into the colour net's A tile;
+//   * a 2-slot ring of A tiles with full/empty mbarriers decouples them, so the latency-bound MMA->epilogue chain (7
+//     dependent stages per tile) hides behind the L1-bound gather instead of serialising with it.
+// Only xyz/dir (24 B) come in and sigma/rgb (16 B) go out per sample.
 #include "grid_common.cuh"
 #include "mlp_tile.cuh"
 #include "sh_poly.cuh"
 
 namespace ntx {
 
-constexpr int kFieldThreads = 256;
+constexpr int kConsumerWarps = 4;
+constexpr int kProducerWarps = 8;
+constexpr int kFieldThreads = 32 * (kConsumerWarps + kProducerWarps);   // 384
 constexpr int kFW = 64;          // hidden width of both MLPs
 constexpr int kColorIn = 32;     // SH(16) + geo_feat(15) + zero pad (network_ff.py:42,95-97)
 constexpr int kFieldMaxLevels = 32;
+constexpr int kStages = 2;
 
 struct FieldPlan {
     uint32_t k0;                 // sigma-net input width = 2L
     uint32_t ws_bytes, wc_bytes; // weight bytes of the two nets
     uint32_t ws_off, wc_off, a0_off, ac_off, h_off, lv_off, misc_off, total;
+    uint32_t a0_stage, ac_stage;
 };
 __host__ __device__ inline FieldPlan field_plan(uint32_t L, uint32_t ns, uint32_t nc) {
     FieldPlan p;
@@ -34,31 +43,37 @@ __host__ __device__ inline FieldPlan field_plan(uint32_t L, uint32_t ns, uint32_
     p.wc_bytes = 2u * (kFW * kColorIn + (nc - 1) * kFW * kFW + 16u * kFW);
     p.ws_off = 0;
     p.wc_off = p.ws_off + p.ws_bytes;
+    p.a0_stage = kTileRows * p.k0 * 2u;
+    p.ac_stage = kTileRows * kColorIn * 2u;
     p.a0_off = (p.wc_off + p.wc_bytes + 127u) & ~127u;
-    p.ac_off = p.a0_off + kTileRows * p.k0 * 2u;
-    p.h_off = p.ac_off + kTileRows * kColorIn * 2u;
+    p.ac_off = p.a0_off + kStages * p.a0_stage;
+    p.h_off = p.ac_off + kStages * p.ac_stage;
     p.lv_off = p.h_off + kTileRows * kFW * 2u;
     p.misc_off = p.lv_off + (uint32_t)sizeof(GridLevel) * kFieldMaxLevels;
-    p.total = p.misc_off + 64u;
+    p.total = p.misc_off + 128u;
     return p;
 }
 
-// hidden-layer epilogue for WIDTH 64 with 8 warps: warp w -> TMEM lane quarter (w&3), column half (w>>2)
-__device__ __forceinline__ void field_hidden_epilogue(uint32_t tmem_base, uint8_t* h_smem) {
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t q = warp & 3, col = (warp >> 2) * 32;
-    const uint32_t row = q * 32 + lane;
-    uint32_t v[32];
-    tc::tmem_ld_x32(tmem_base + ((q * 32u) << 16) + col, v);
-    tc::tmem_wait_ld();
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kConsumerWarps) : "memory"); }
+
+// hidden-layer epilogue (4 consumer warps, warp w owns TMEM lanes 32w..32w+31 = tile rows): two 32-column passes
+__device__ __forceinline__ void field_hidden_epilogue(uint32_t tmem_base, uint8_t* h_smem, uint32_t warp, uint32_t lane) {
+    const uint32_t row = warp * 32 + lane;
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-        uint4 o;
-        o.x = act_pack2(0, v[j + 0], v[j + 1]);
-        o.y = act_pack2(0, v[j + 2], v[j + 3]);
-        o.z = act_pack2(0, v[j + 4], v[j + 5]);
-        o.w = act_pack2(0, v[j + 6], v[j + 7]);
-        *reinterpret_cast<uint4*>(h_smem + kmajor_chunk_off(row, (col + j) >> 3, kFW)) = o;
+    for (int half_sel = 0; half_sel < 2; half_sel++) {
+        const uint32_t col = half_sel * 32;
+        uint32_t v[32];
+        tc::tmem_ld_x32(tmem_base + ((warp * 32u) << 16) + col, v);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            uint4 o;
+            o.x = act_pack2(0, v[j + 0], v[j + 1]);
+            o.y = act_pack2(0, v[j + 2], v[j + 3]);
+            o.z = act_pack2(0, v[j + 4], v[j + 5]);
+            o.w = act_pack2(0, v[j + 6], v[j + 7]);
+            *reinterpret_cast<uint4*>(h_smem + kmajor_chunk_off(row, (col + j) >> 3, kFW)) = o;
+        }
     }
 }
 
@@ -66,23 +81,29 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
     const float* __restrict__ xyz, const float* __restrict__ dirs, const float* __restrict__ deltas, const uint32_t M, const float bound,
     const __half* __restrict__ table, const int* __restrict__ offsets, const uint32_t L, const float S, const uint32_t H, const bool align,
     const __half* __restrict__ w_sigma, const __half* __restrict__ w_color, const uint32_t ns, const uint32_t nc, const float density_scale,
-    float* __restrict__ sigmas, float* __restrict__ rgbs) {
+    float* __restrict__ sigmas, float* __restrict__ rgbs, const uint32_t keep_bytes) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const FieldPlan plan = field_plan(L, ns, nc);
     uint8_t* ws_smem = smem + plan.ws_off;
     uint8_t* wc_smem = smem + plan.wc_off;
-    uint8_t* a0_smem = smem + plan.a0_off;
-    uint8_t* ac_smem = smem + plan.ac_off;
+    uint8_t* a0_smem = smem + plan.a0_off;   // kStages tiles
+    uint8_t* ac_smem = smem + plan.ac_off;   // kStages tiles
     uint8_t* h_smem = smem + plan.h_off;
     GridLevel* lv = reinterpret_cast<GridLevel*>(smem + plan.lv_off);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + plan.misc_off);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + plan.misc_off + 16);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + plan.misc_off);        // [kStages] producers -> consumer
+    uint64_t* empty_bar = full_bar + kStages;                                      // [kStages] consumer (MMA completion) -> producers
+    uint64_t* mma_bar = empty_bar + kStages;                                       // layer done -> consumer warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t K0 = plan.k0;
 
-    // ---- one-time setup --------------------------------------------------------------------------------------
-    if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_mbar_init(); }
+    // ---- one-time setup (all 12 warps) ---------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int s = 0; s < kStages; s++) { tc::mbar_init(&full_bar[s], kProducerWarps); tc::mbar_init(&empty_bar[s], 1); }
+        tc::mbar_init(mma_bar, 1);
+        tc::fence_mbar_init();
+    }
     if (warp == 0) tc::tmem_alloc<64>(tmem_slot);
     if (tid < L) lv[tid] = make_level<3>(offsets, tid, S, H, /*gridtype=*/0, align);
     {
@@ -100,23 +121,21 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
     __syncthreads();
     tc::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t ws_addr = tc::smem_u32(ws_smem), wc_addr = tc::smem_u32(wc_smem);
-    const uint32_t a0_addr = tc::smem_u32(a0_smem), ac_addr = tc::smem_u32(ac_smem), h_addr = tc::smem_u32(h_smem);
-    uint32_t phase = 0;
-
-    const float half_off = align ? 0.0f : 0.5f;
-    // GridEncoder.forward: inputs = (inputs + bound) / (2 * bound) (grid.py:143).  torch's CUDA true-division by a Python
-    // scalar multiplies by the fp32 reciprocal (BinaryDivTrueKernel.cu), so do exactly that.
-    const float inv2b = 1.0f / (2.0f * bound);
-    const uint32_t p = tid & 1u;
-    const uint32_t srow = tid >> 1;  // sample row of this lane pair inside the tile
-
     const uint32_t ntiles = ceil_div<uint32_t>(M, kTileRows);
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint32_t row0 = tile * kTileRows;
-        // ---------------- gather phase: features -> A0, SH -> Ac[:, 0:16] ------------------------------------
-        {
-            const uint32_t b = row0 + srow;
+
+    if (warp >= kConsumerWarps) {
+        // =============================== PRODUCERS: gather + SH =====================================================
+        const uint32_t ptid = tid - 32 * kConsumerWarps;      // 0..255
+        const uint32_t p = ptid & 1u;                          // which x corner this lane gathers
+        const uint32_t srow = ptid >> 1;                       // sample row of this lane pair inside the tile
+        const float half_off = align ? 0.0f : 0.5f;
+        // GridEncoder.forward: inputs = (inputs + bound) / (2 * bound) (grid.py:143).  torch's CUDA true-division by a Python
+        // scalar multiplies by the fp32 reciprocal (BinaryDivTrueKernel.cu), so do exactly that.
+        const float inv2b = 1.0f / (2.0f * bound);
+        uint32_t k = 0;
+        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+            const uint32_t s = k % kStages, use = k / kStages;
+            const uint32_t b = tile * kTileRows + srow;
             const bool valid = b < M;
             float x = 0.f, y = 0.f, z = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
             bool skip = !valid;
@@ -129,12 +148,16 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
             }
             const bool oob = (x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1);
             const bool live = !skip && !oob;
+            if (!live) { x = 0.f; y = 0.f; z = 0.f; }  // keeps the (discarded) loads of dead lanes in bounds
+            tc::mbar_wait(&empty_bar[s], (use & 1u) ^ 1u);   // slot free? (first use of a slot passes immediately)
+            uint8_t* a0 = a0_smem + s * plan.a0_stage;
+            uint8_t* ac = ac_smem + s * plan.ac_stage;
             for (uint32_t l0 = 0; l0 < L; l0 += 4) {
                 uint32_t packed[2];
-                pair_gather4<__half>(x, y, z, live, p, lv + l0, table, half_off, packed);
+                pair_gather4<__half>(x, y, z, live, p, lv + l0, table, half_off, keep_bytes, packed);
                 // lane p owns levels l0+2p, l0+2p+1 -> 4 consecutive halfs (8 bytes) of the row
-                const uint32_t k = 2 * (l0 + 2 * p);
-                *reinterpret_cast<uint2*>(a0_smem + kmajor_off(srow, k, K0)) = make_uint2(packed[0], packed[1]);
+                const uint32_t kcol = 2 * (l0 + 2 * p);
+                *reinterpret_cast<uint2*>(a0 + kmajor_off(srow, kcol, K0)) = make_uint2(packed[0], packed[1]);
             }
             // SH of the view direction (fp32, rounded to fp16 when it enters the fp16 MLP): lane p writes 8 of the 16 values
             float sh[16];
@@ -144,91 +167,105 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
             o.y = float2_to_half2_bits(sh[8 * p + 2], sh[8 * p + 3]);
             o.z = float2_to_half2_bits(sh[8 * p + 4], sh[8 * p + 5]);
             o.w = float2_to_half2_bits(sh[8 * p + 6], sh[8 * p + 7]);
-            *reinterpret_cast<uint4*>(ac_smem + kmajor_chunk_off(srow, p, kColorIn)) = o;
+            *reinterpret_cast<uint4*>(ac + kmajor_chunk_off(srow, p, kColorIn)) = o;
+            tc::fence_proxy_async_smem();          // my generic-proxy writes -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&full_bar[s]);
         }
-        tc::fence_proxy_async_smem();
-        __syncthreads();
-
-        // ---------------- sigma net ----------------------------------------------------------------------------
-        if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(a0_addr, ws_addr, K0, kFW, tmem_base); tc::mma_commit(bar); }
-        tc::mbar_wait(bar, phase); phase ^= 1;
-        tc::tc_fence_after_sync();
-        field_hidden_epilogue(tmem_base, h_smem);
-        tc::fence_proxy_async_smem(); tc::tc_fence_before_sync(); __syncthreads();
-        uint32_t w_off = kFW * K0 * 2u;
-        for (uint32_t k = 0; k + 1 < ns; k++) {
-            if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(h_addr, ws_addr + w_off, kFW, kFW, tmem_base); tc::mma_commit(bar); }
-            tc::mbar_wait(bar, phase); phase ^= 1;
-            tc::tc_fence_after_sync();
-            field_hidden_epilogue(tmem_base, h_smem);
-            tc::fence_proxy_async_smem(); tc::tc_fence_before_sync(); __syncthreads();
-            w_off += kFW * kFW * 2u;
-        }
-        if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(h_addr, ws_addr + w_off, kFW, 16, tmem_base); tc::mma_commit(bar); }
-        tc::mbar_wait(bar, phase); phase ^= 1;
-        tc::tc_fence_after_sync();
-        if (warp < 4) {
-            uint32_t v[16];
-            tc::tmem_ld_x16(tmem_base + ((warp * 32u) << 16), v);
-            tc::tmem_wait_ld();
+    } else {
+        // =============================== CONSUMERS: the two MLPs =====================================================
+        const uint32_t ws_addr = tc::smem_u32(ws_smem), wc_addr = tc::smem_u32(wc_smem), h_addr = tc::smem_u32(h_smem);
+        uint32_t mma_phase = 0;
+        uint32_t k = 0;
+        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+            const uint32_t s = k % kStages, use = k / kStages;
+            const uint32_t a0_addr = tc::smem_u32(a0_smem + s * plan.a0_stage), ac_addr = tc::smem_u32(ac_smem + s * plan.ac_stage);
+            uint8_t* ac = ac_smem + s * plan.ac_stage;
             const uint32_t row = warp * 32 + lane;
-            // h = fp16(W2 . a)   (FFMLP output is fp16); sigma = trunc_exp(h[0]) = exp(float(h[0]))   (network_ff.py:88)
-            uint32_t hb[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) hb[j] = float2_to_half2_bits(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-            const float h0 = __low2float(*reinterpret_cast<const __half2*>(&hb[0]));
-            const uint32_t b = row0 + row;
-            if (b < M) {
-                const bool dead = deltas && deltas[(size_t)b * 2] == 0.0f;
-                st_stream_f32(sigmas + b, dead ? 0.0f : density_scale * expf(h0));
-            }
-            // colour-net input columns 16..31 = h[1..15], 0   (network_ff.py:95-97)
-            uint4 c2, c3;
-            c2.x = __byte_perm(hb[0], hb[1], 0x5432); c2.y = __byte_perm(hb[1], hb[2], 0x5432);
-            c2.z = __byte_perm(hb[2], hb[3], 0x5432); c2.w = __byte_perm(hb[3], hb[4], 0x5432);
-            c3.x = __byte_perm(hb[4], hb[5], 0x5432); c3.y = __byte_perm(hb[5], hb[6], 0x5432);
-            c3.z = __byte_perm(hb[6], hb[7], 0x5432); c3.w = __byte_perm(hb[7], 0u, 0x5432);
-            *reinterpret_cast<uint4*>(ac_smem + kmajor_chunk_off(row, 2, kColorIn)) = c2;
-            *reinterpret_cast<uint4*>(ac_smem + kmajor_chunk_off(row, 3, kColorIn)) = c3;
-        }
-        tc::fence_proxy_async_smem(); tc::tc_fence_before_sync(); __syncthreads();
+            const uint32_t b = tile * kTileRows + row;
+            const bool dead = (b >= M) || (deltas && deltas[(size_t)b * 2] == 0.0f);
 
-        // ---------------- colour net ---------------------------------------------------------------------------
-        if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(ac_addr, wc_addr, kColorIn, kFW, tmem_base); tc::mma_commit(bar); }
-        tc::mbar_wait(bar, phase); phase ^= 1;
-        tc::tc_fence_after_sync();
-        field_hidden_epilogue(tmem_base, h_smem);
-        tc::fence_proxy_async_smem(); tc::tc_fence_before_sync(); __syncthreads();
-        w_off = kFW * kColorIn * 2u;
-        for (uint32_t k = 0; k + 1 < nc; k++) {
-            if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(h_addr, wc_addr + w_off, kFW, kFW, tmem_base); tc::mma_commit(bar); }
-            tc::mbar_wait(bar, phase); phase ^= 1;
+            tc::mbar_wait(&full_bar[s], use & 1u);
             tc::tc_fence_after_sync();
-            field_hidden_epilogue(tmem_base, h_smem);
-            tc::fence_proxy_async_smem(); tc::tc_fence_before_sync(); __syncthreads();
-            w_off += kFW * kFW * 2u;
-        }
-        if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(h_addr, wc_addr + w_off, kFW, 16, tmem_base); tc::mma_commit(bar); }
-        tc::mbar_wait(bar, phase); phase ^= 1;
-        tc::tc_fence_after_sync();
-        if (warp < 4) {
-            uint32_t v[8];
-            tc::tmem_ld_x8(tmem_base + ((warp * 32u) << 16), v);
-            tc::tmem_wait_ld();
-            const uint32_t b = row0 + warp * 32 + lane;
-            if (b < M) {
-                const bool dead = deltas && deltas[(size_t)b * 2] == 0.0f;
+            // ---------------- sigma net ------------------------------------------------------------------------
+            if (tid == 0) { issue_layer(a0_addr, ws_addr, K0, kFW, tmem_base); tc::mma_commit(mma_bar); }
+            tc::mbar_wait(mma_bar, mma_phase); mma_phase ^= 1;
+            tc::tc_fence_after_sync();
+            field_hidden_epilogue(tmem_base, h_smem, warp, lane);
+            tc::fence_proxy_async_smem(); tc::tc_fence_before_sync(); consumer_sync();
+            uint32_t w_off = kFW * K0 * 2u;
+            for (uint32_t j = 0; j + 1 < ns; j++) {
+                if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(h_addr, ws_addr + w_off, kFW, kFW, tmem_base); tc::mma_commit(mma_bar); }
+                tc::mbar_wait(mma_bar, mma_phase); mma_phase ^= 1;
+                tc::tc_fence_after_sync();
+                field_hidden_epilogue(tmem_base, h_smem, warp, lane);
+                tc::fence_proxy_async_smem(); tc::tc_fence_before_sync(); consumer_sync();
+                w_off += kFW * kFW * 2u;
+            }
+            if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(h_addr, ws_addr + w_off, kFW, 16, tmem_base); tc::mma_commit(mma_bar); }
+            tc::mbar_wait(mma_bar, mma_phase); mma_phase ^= 1;
+            tc::tc_fence_after_sync();
+            {
+                uint32_t v[16];
+                tc::tmem_ld_x16(tmem_base + ((warp * 32u) << 16), v);
+                tc::tmem_wait_ld();
+                // h = fp16(W2 . a)   (FFMLP output is fp16); sigma = trunc_exp(h[0]) = exp(float(h[0]))   (network_ff.py:88)
+                uint32_t hb[8];
 #pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    // rgb = sigmoid(h) evaluated on the fp16 output in fp32 and rounded back to fp16 (torch.sigmoid on a half tensor)
-                    const float hc = __half2float(__float2half_rn(__uint_as_float(v[c])));
-                    const float sg = 1.0f / (1.0f + expf(-hc));
-                    st_stream_f32(rgbs + (size_t)b * 3 + c, dead ? 0.0f : __half2float(__float2half_rn(sg)));
+                for (int j = 0; j < 8; j++) hb[j] = float2_to_half2_bits(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                const float h0 = __low2float(*reinterpret_cast<const __half2*>(&hb[0]));
+                if (b < M) st_stream_f32(sigmas + b, dead ? 0.0f : density_scale * expf(h0));
+                // colour-net input columns 16..31 = h[1..15], 0   (network_ff.py:95-97)
+                uint4 c2, c3;
+                c2.x = __byte_perm(hb[0], hb[1], 0x5432); c2.y = __byte_perm(hb[1], hb[2], 0x5432);
+                c2.z = __byte_perm(hb[2], hb[3], 0x5432); c2.w = __byte_perm(hb[3], hb[4], 0x5432);
+                c3.x = __byte_perm(hb[4], hb[5], 0x5432); c3.y = __byte_perm(hb[5], hb[6], 0x5432);
+                c3.z = __byte_perm(hb[6], hb[7], 0x5432); c3.w = __byte_perm(hb[7], 0u, 0x5432);
+                *reinterpret_cast<uint4*>(ac + kmajor_chunk_off(row, 2, kColorIn)) = c2;
+                *reinterpret_cast<uint4*>(ac + kmajor_chunk_off(row, 3, kColorIn)) = c3;
+            }
+            tc::fence_proxy_async_smem(); tc::tc_fence_before_sync(); consumer_sync();
+
+            // ---------------- colour net -----------------------------------------------------------------------
+            if (tid == 0) {
+                tc::tc_fence_after_sync();
+                issue_layer(ac_addr, wc_addr, kColorIn, kFW, tmem_base);
+                tc::mma_commit(mma_bar);
+                tc::mma_commit(&empty_bar[s]);   // both A tiles of this slot have been consumed once these MMAs retire
+            }
+            tc::mbar_wait(mma_bar, mma_phase); mma_phase ^= 1;
+            tc::tc_fence_after_sync();
+            field_hidden_epilogue(tmem_base, h_smem, warp, lane);
+            tc::fence_proxy_async_smem(); tc::tc_fence_before_sync(); consumer_sync();
+            w_off = kFW * kColorIn * 2u;
+            for (uint32_t j = 0; j + 1 < nc; j++) {
+                if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(h_addr, wc_addr + w_off, kFW, kFW, tmem_base); tc::mma_commit(mma_bar); }
+                tc::mbar_wait(mma_bar, mma_phase); mma_phase ^= 1;
+                tc::tc_fence_after_sync();
+                field_hidden_epilogue(tmem_base, h_smem, warp, lane);
+                tc::fence_proxy_async_smem(); tc::tc_fence_before_sync(); consumer_sync();
+                w_off += kFW * kFW * 2u;
+            }
+            if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(h_addr, wc_addr + w_off, kFW, 16, tmem_base); tc::mma_commit(mma_bar); }
+            tc::mbar_wait(mma_bar, mma_phase); mma_phase ^= 1;
+            tc::tc_fence_after_sync();
+            {
+                uint32_t v[8];
+                tc::tmem_ld_x8(tmem_base + ((warp * 32u) << 16), v);
+                tc::tmem_wait_ld();
+                if (b < M) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        // rgb = sigmoid(h) evaluated on the fp16 output in fp32 and rounded back to fp16 (torch.sigmoid on a half tensor)
+                        const float hc = __half2float(__float2half_rn(__uint_as_float(v[c])));
+                        const float sg = 1.0f / (1.0f + expf(-hc));
+                        st_stream_f32(rgbs + (size_t)b * 3 + c, dead ? 0.0f : __half2float(__float2half_rn(sg)));
+                    }
                 }
             }
+            tc::tc_fence_before_sync();
+            consumer_sync();   // TMEM accumulator is reused by the next tile's first MMA
         }
-        tc::tc_fence_before_sync();
-        __syncthreads();
     }
 
     tc::tc_fence_before_sync();
@@ -262,16 +299,15 @@ extern "C" int ntx_ngp_field_forward(const float* xyz, const float* dirs, const 
         occ = 0;
     }
     if (!occ) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ngp_field_kernel, kFieldThreads, plan.total) != cudaSuccess || occ < 1) occ = 1;
-        occ = std::min(occ, 512 / 64);
+        occ = resident_ctas_per_sm((const void*)ngp_field_kernel, kFieldThreads, plan.total, 64);
+        if (tunables().field_ctas > 0) occ = std::min(occ, tunables().field_ctas);
     }
-    int dev = 0, sms = kNumSMs;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = device_sm_count();
     const uint32_t ntiles = ceil_div<uint32_t>(M, kTileRows);
     const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)(occ * sms));
     ngp_field_kernel<<<grid, kFieldThreads, plan.total, reinterpret_cast<cudaStream_t>(stream)>>>(
         xyz, dirs, deltas, M, bound, static_cast<const __half*>(embeddings_f16), offsets, L, S, H, align_corners != 0,
-        static_cast<const __half*>(w_sigma_f16), static_cast<const __half*>(w_color_f16), ns, nc, density_scale, sigmas, rgbs);
+        static_cast<const __half*>(w_sigma_f16), static_cast<const __half*>(w_color_f16), ns, nc, density_scale, sigmas, rgbs,
+        tunables().l1_keep_bytes);
     return check_launch("ngp_field_forward");
 }

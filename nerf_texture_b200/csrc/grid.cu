@@ -139,7 +139,7 @@ template <typename scalar_t>
 __global__ void __launch_bounds__(kPairThreads, 3) grid_fwd_pair_kernel(
     const float* __restrict__ inputs, const scalar_t* __restrict__ grid, const int* __restrict__ offsets,
     scalar_t* __restrict__ outputs, const uint32_t B, const uint32_t L, const float S, const uint32_t H,
-    const uint32_t gridtype, const bool align, const int layout) {
+    const uint32_t gridtype, const bool align, const int layout, const uint32_t keep_bytes) {
     using E = Elem2<scalar_t>;
     using raw = typename E::raw;
     __shared__ GridLevel lv[kPairMaxLevels];
@@ -156,10 +156,11 @@ __global__ void __launch_bounds__(kPairThreads, 3) grid_fwd_pair_kernel(
         if (valid) { x = inputs[(size_t)b * 3]; y = inputs[(size_t)b * 3 + 1]; z = inputs[(size_t)b * 3 + 2]; }
         const bool oob = (x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1);
         const bool live = valid && !oob;
+        if (!live) { x = 0.f; y = 0.f; z = 0.f; }  // keeps the (discarded) loads of dead lanes in bounds
 
         for (uint32_t l0 = 0; l0 < L; l0 += 4) {
             raw packed[2];
-            pair_gather4<scalar_t>(x, y, z, live, p, lv + l0, grid, half_off, packed);
+            pair_gather4<scalar_t>(x, y, z, live, p, lv + l0, grid, half_off, keep_bytes, packed);
             if (valid) {
                 const uint32_t la = l0 + 2 * p;
                 if (layout == NTX_LAYOUT_BLC) {
@@ -313,9 +314,13 @@ template <typename scalar_t>
 static int launch_fwd_pair(const float* inputs, const scalar_t* emb, const int* offsets, scalar_t* out, uint32_t B, uint32_t L, float S,
                            uint32_t H, uint32_t gridtype, bool align, int layout, cudaStream_t st) {
     static int grid_cap = 0;
-    if (!grid_cap) grid_cap = persistent_grid((const void*)grid_fwd_pair_kernel<scalar_t>, kPairThreads, 0);
+    if (!grid_cap) {
+        grid_cap = persistent_grid((const void*)grid_fwd_pair_kernel<scalar_t>, kPairThreads, 0);
+        if (tunables().pair_ctas > 0) grid_cap = tunables().pair_ctas * device_sm_count();
+    }
     const uint32_t groups = ceil_div<uint32_t>(B, kPairThreads / 2);
-    grid_fwd_pair_kernel<scalar_t><<<min(groups, (uint32_t)grid_cap), kPairThreads, 0, st>>>(inputs, emb, offsets, out, B, L, S, H, gridtype, align, layout);
+    grid_fwd_pair_kernel<scalar_t><<<min(groups, (uint32_t)grid_cap), kPairThreads, 0, st>>>(inputs, emb, offsets, out, B, L, S, H, gridtype, align, layout,
+                                                                                             tunables().l1_keep_bytes);
     return check_launch("grid_encode_forward(pair)");
 }
 

@@ -60,32 +60,44 @@ __device__ __forceinline__ uint32_t corner_index(const GridLevel& g, const uint3
     return wrap_index(g, index);
 }
 
+// out-of-line so that the compiler keeps the (almost never taken) modulo behind a real branch instead of if-converting a
+// 20-instruction integer division into every corner of every level
+static __device__ __noinline__ uint32_t slow_umod(uint32_t a, uint32_t b) { return a % b; }
+
 // ---------------------------------------------------------------------------------------------------- lane-pair gather
 // D = 3, C = 2.  Raw table element = 2 scalars: u32 for half2, u64 for float2.
 template <typename scalar_t> struct Elem2;
 template <> struct Elem2<__half> {
     using raw = uint32_t;
-    static __device__ __forceinline__ raw load(const void* p) { return ld_table_u32(p); }
-    static __device__ __forceinline__ raw xchg(raw v) { return __shfl_xor_sync(0xffffffffu, v, 1); }
-    struct accum { __half a, b; };
-    static __device__ __forceinline__ accum zero() { return {__float2half_rn(0.f), __float2half_rn(0.f)}; }
-    static __device__ __forceinline__ void add(accum& r, float w, raw v) {
-        const float2 f = half2_bits_to_float2(v);
-        // p = half(w*g); r = half(float(r)+float(p))  per channel (c10::Half rounding points)
-        const __half2 p = __floats2half2_rn(w * f.x, w * f.y);
-        const float2 pf = __half22float2(p);
-        r.a = __float2half_rn(__half2float(r.a) + pf.x);
-        r.b = __float2half_rn(__half2float(r.b) + pf.y);
+    using accum = __half2;
+    // hashed levels are far larger than L1 and touched at random: do not let them evict the small dense levels
+    static __device__ __forceinline__ raw load(const void* p, bool keep_l1) {
+        raw r;
+        if (keep_l1) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
+        else asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+        return r;
     }
-    static __device__ __forceinline__ raw pack(const accum& r) { __half2 h = __halves2half2(r.a, r.b); return *reinterpret_cast<const uint32_t*>(&h); }
+    static __device__ __forceinline__ raw xchg(raw v) { return __shfl_xor_sync(0xffffffffu, v, 1); }
+    static __device__ __forceinline__ accum zero() { return __floats2half2_rn(0.f, 0.f); }
+    static __device__ __forceinline__ void add(accum& r, float w, raw v) {
+        // reference (c10::Half): p = half(w * float(g)); r = half(float(r) + float(p)).  The second step equals one
+        // correctly-rounded fp16 add for every pair of finite halves (checked exhaustively, tests/test_oracle_cpu.py),
+        // so HADD2 does both channels in one instruction.
+        const float2 f = half2_bits_to_float2(v);
+        r = __hadd2(r, __floats2half2_rn(w * f.x, w * f.y));
+    }
+    static __device__ __forceinline__ raw pack(const accum& r) { return *reinterpret_cast<const uint32_t*>(&r); }
 };
 template <> struct Elem2<float> {
     using raw = uint64_t;
-    static __device__ __forceinline__ raw load(const void* p) {
-        raw r; asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(r) : "l"(p)); return r;
+    struct accum { float a, b; };
+    static __device__ __forceinline__ raw load(const void* p, bool keep_l1) {
+        raw r;
+        if (keep_l1) asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(r) : "l"(p));
+        else asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(p));
+        return r;
     }
     static __device__ __forceinline__ raw xchg(raw v) { return __shfl_xor_sync(0xffffffffu, v, 1); }
-    struct accum { float a, b; };
     static __device__ __forceinline__ accum zero() { return {0.f, 0.f}; }
     static __device__ __forceinline__ void add(accum& r, float w, raw v) {
         const float lo = __uint_as_float((uint32_t)v), hi = __uint_as_float((uint32_t)(v >> 32));
@@ -98,10 +110,12 @@ template <> struct Elem2<float> {
 // A lane pair (lanes 2i, 2i+1) owns one sample; lane p (= lane & 1) gathers the four corners whose x bit is p.
 // Processes the 4 consecutive levels lv[0..3]; on return lane p holds the finished features of levels 2p and 2p+1
 // (packed[0], packed[1]), accumulated over the 8 corners in exactly the reference's order and rounding.
-// Must be called by all 32 lanes of the warp (uses shuffles).  `live` = sample valid and inside [0,1]^3.
+// Must be called by all 32 lanes of the warp (uses shuffles).  `live` = sample valid and inside [0,1]^3; coordinates of
+// non-live samples must have been forced to 0 by the caller (their loads then hit entry 0 of each level and are discarded).
 template <typename scalar_t>
 __device__ __forceinline__ void pair_gather4(const float x, const float y, const float z, const bool live, const uint32_t p, const GridLevel* __restrict__ lv,
-                                             const scalar_t* __restrict__ grid, const float half_off, typename Elem2<scalar_t>::raw packed[2]) {
+                                             const scalar_t* __restrict__ grid, const float half_off, const uint32_t keep_bytes,
+                                             typename Elem2<scalar_t>::raw packed[2]) {
     using E = Elem2<scalar_t>;
     using raw = typename E::raw;
     raw v[4][4];
@@ -114,15 +128,26 @@ __device__ __forceinline__ void pair_gather4(const float x, const float y, const
         fx[j] = px - flx; fy[j] = py - fly; fz[j] = pz - flz;
         const uint32_t cx = (uint32_t)flx + p, iy = (uint32_t)fly, iz = (uint32_t)flz;
         const scalar_t* gl = grid + (size_t)g.offset * 2;
-        uint32_t ty0, ty1, tz0, tz1;
-        if (g.use_hash) { ty0 = iy * 2654435761u; ty1 = ty0 + 2654435761u; tz0 = iz * 805459861u; tz1 = tz0 + 805459861u; }
-        else { ty0 = iy * g.sy; ty1 = ty0 + g.sy; tz0 = iz * g.sz; tz1 = tz0 + g.sz; }
+        const bool keep = g.hs * (uint32_t)(2 * sizeof(scalar_t)) <= keep_bytes;  // whole level small enough to live in L1
+        if (g.use_hash && g.mask) {           // hashed level, power-of-two table: the hot path for fine levels
+            const uint32_t ty0 = iy * 2654435761u, ty1 = ty0 + 2654435761u, tz0 = iz * 805459861u, tz1 = tz0 + 805459861u;
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const uint32_t ty = (c & 1) ? ty1 : ty0, tz = (c & 2) ? tz1 : tz0;
-            const uint32_t index = wrap_index(g, g.use_hash ? (cx ^ ty ^ tz) : (cx + ty + tz));
-            // out-of-range / padding lanes read entry 0 of the level (always mapped) and discard it
-            v[j][c] = E::load(gl + (size_t)(live ? index : 0u) * 2);
+            for (int c = 0; c < 4; c++) {
+                const uint32_t index = (cx ^ ((c & 1) ? ty1 : ty0) ^ ((c & 2) ? tz1 : tz0)) & g.mask;
+                v[j][c] = E::load(gl + (size_t)index * 2, keep);
+            }
+        } else {
+            uint32_t ty0, ty1, tz0, tz1;
+            if (g.use_hash) { ty0 = iy * 2654435761u; ty1 = ty0 + 2654435761u; tz0 = iz * 805459861u; tz1 = tz0 + 805459861u; }
+            else { ty0 = iy * g.sy; ty1 = ty0 + g.sy; tz0 = iz * g.sz; tz1 = tz0 + g.sz; }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const uint32_t ty = (c & 1) ? ty1 : ty0, tz = (c & 2) ? tz1 : tz0;
+                uint32_t index = g.use_hash ? (cx ^ ty ^ tz) : (cx + ty + tz);
+                // dense levels only leave [0, hs) when a coordinate is exactly 1.0 (corner res) — rare, keep it a branch
+                if (__builtin_expect(index >= g.hs, 0)) index = g.mask ? (index & g.mask) : slow_umod(index, g.hs);
+                v[j][c] = E::load(gl + (size_t)index * 2, keep);
+            }
         }
     }
     // lane p accumulates levels 2p and 2p+1 of the batch; it needs the partner's corners of those levels
@@ -134,16 +159,18 @@ __device__ __forceinline__ void pair_gather4(const float x, const float y, const
 #pragma unroll
     for (int jj = 0; jj < 2; jj++) {
         const float wfx = p ? fx[2 + jj] : fx[jj], wfy = p ? fy[2 + jj] : fy[jj], wfz = p ? fz[2 + jj] : fz[jj];
+        const float wx0 = 1 - wfx, wy0 = 1 - wfy, wz0 = 1 - wfz;
+        // reference order: idx = bx + 2*by + 4*bz, w = ((1*wx)*wy)*wz   (gridencoder.cu:146-167)
+        const float w00 = wx0 * wy0, w10 = wfx * wy0, w01 = wx0 * wfy, w11 = wfx * wfy;
         typename E::accum r = E::zero();
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const float wy = (c & 1) ? wfy : 1 - wfy, wz = (c & 2) ? wfz : 1 - wfz;
+            const float wz = (c & 2) ? wfz : wz0;
             const raw mine = p ? v[2 + jj][c] : v[jj][c];
             const raw x0v = p ? o[jj][c] : mine;   // corner with x bit 0
             const raw x1v = p ? mine : o[jj][c];   // corner with x bit 1
-            // reference order: idx = bx + 2*by + 4*bz, w = ((1*wx)*wy)*wz   (gridencoder.cu:146-167)
-            E::add(r, ((1 - wfx) * wy) * wz, x0v);
-            E::add(r, (wfx * wy) * wz, x1v);
+            E::add(r, ((c & 1) ? w01 : w00) * wz, x0v);
+            E::add(r, ((c & 1) ? w11 : w10) * wz, x1v);
         }
         packed[jj] = live ? E::pack(r) : (raw)0;
     }

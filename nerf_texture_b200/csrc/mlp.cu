@@ -170,12 +170,9 @@ static int launch_mlp(const __half* in, const __half* w, __half* out, __half* fw
         }
         configured_smem = (int)plan.total;
     }
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kMlpThreads, plan.total) != cudaSuccess || occ < 1) occ = 1;
     constexpr int TM_COLS = WIDTH < 32 ? 32 : WIDTH;
-    occ = std::min(occ, 512 / TM_COLS);  // TMEM columns are a per-SM resource too
-    int dev = 0, sms = kNumSMs;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    occ = resident_ctas_per_sm((const void*)kern, kMlpThreads, plan.total, TM_COLS);
+    const int sms = device_sm_count();
     const uint32_t ntiles = ceil_div<uint32_t>(B, kTileRows);
     const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)(occ * sms));
     kern<<<grid, kMlpThreads, plan.total, st>>>(in, w, out, fwd, B, in_dim, num_layers, act, out_act);

@@ -478,6 +478,79 @@ __global__ void __launch_bounds__(128) march_rays_kernel(const uint32_t n_alive,
     }
 }
 
+// Same marcher, but every thread parks its (at most 8) samples in shared memory first and the block then writes its three
+// contiguous output segments with coalesced 16-byte stores.  (One thread per ray emits 32 B per sample at a stride of
+// n_step*32 B between lanes: written directly that is ~29 scattered sectors per warp store and the LSU queue becomes the
+// bottleneck — 106 us per loop iteration in the first ncu capture, profiles/r01_frame_kernels.md.)
+constexpr int kMarchThreads = 128;
+constexpr uint32_t kMarchMaxStagedSteps = 8;
+
+__device__ __forceinline__ void block_copy_out(float* __restrict__ dst, const float* __restrict__ src, uint32_t nfloats) {
+    // dst is 16-byte aligned for every block (segment starts at a multiple of 128 rows)
+    const uint32_t nvec = nfloats >> 2;
+    for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) st_stream_u4(dst + 4 * i, *reinterpret_cast<const uint4*>(src + 4 * i));
+    for (uint32_t i = (nvec << 2) + threadIdx.x; i < nfloats; i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
+    const uint32_t n_alive, const uint32_t n_step, const int* __restrict__ rays_alive, const float* __restrict__ rays_t, const float* __restrict__ rays_o,
+    const float* __restrict__ rays_d, const float bound, const float dt_gamma, const uint32_t max_steps, const uint32_t C, const uint32_t H,
+    const uint8_t* __restrict__ grid, const float* __restrict__ nears, const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs,
+    float* __restrict__ deltas, const uint32_t perturb, const uint32_t M_padded) {
+    extern __shared__ __align__(16) float stage[];          // [128*n_step*3] xyz | [128*n_step*3] dir | [128*n_step*2] delta
+    float* sx = stage;
+    float* sd = stage + kMarchThreads * n_step * 3;
+    float* sl = sd + kMarchThreads * n_step * 3;
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    {   // padding rows beyond n_alive*n_step (align-to-128 tail, raymarching.py:386-387)
+        const uint32_t row = n_alive * n_step + n;
+        if (row < M_padded) {
+            xyzs[(size_t)row * 3] = 0; xyzs[(size_t)row * 3 + 1] = 0; xyzs[(size_t)row * 3 + 2] = 0;
+            dirs[(size_t)row * 3] = 0; dirs[(size_t)row * 3 + 1] = 0; dirs[(size_t)row * 3 + 2] = 0;
+            deltas[(size_t)row * 2] = 0; deltas[(size_t)row * 2 + 1] = 0;
+        }
+    }
+    const uint32_t first = blockIdx.x * kMarchThreads;
+    if (first >= n_alive) return;                            // block only had padding rows to clear
+    if (n < n_alive) {
+        const int index = rays_alive[n];
+        float t = rays_t[n];
+        const Ray r = load_ray(rays_o + (size_t)index * 3, rays_d + (size_t)index * 3);
+        const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H, grid);
+        float* px = sx + threadIdx.x * n_step * 3;
+        float* pd = sd + threadIdx.x * n_step * 3;
+        float* pl = sl + threadIdx.x * n_step * 2;
+        const float far = fars[index];
+        if (perturb) {
+            Pcg32 rng; rng.seed((uint64_t)perturb);   // raymarching.cu:1011
+            rng.advance(n);
+            t += p.dt_min * rng.next_float();
+        }
+        float last_t = t, x, y, z, dt;
+        uint32_t step = 0;
+        while (t < far && step < n_step) {
+            if (probe(r, p, t, x, y, z, dt)) {
+                px[0] = x; px[1] = y; px[2] = z;
+                pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+                t += dt;
+                pl[0] = dt; pl[1] = t - last_t;
+                last_t = t;
+                px += 3; pd += 3; pl += 2; step++;
+            }
+        }
+        for (; step < n_step; step++) {                      // unused slots: zero (delta == 0 is composite_rays' stop sentinel)
+            px[0] = 0; px[1] = 0; px[2] = 0; pd[0] = 0; pd[1] = 0; pd[2] = 0; pl[0] = 0; pl[1] = 0;
+            px += 3; pd += 3; pl += 2;
+        }
+    }
+    __syncthreads();
+    const uint32_t rays_here = min((uint32_t)kMarchThreads, n_alive - first);
+    const size_t row0 = (size_t)first * n_step;
+    block_copy_out(xyzs + row0 * 3, sx, rays_here * n_step * 3);
+    block_copy_out(dirs + row0 * 3, sd, rays_here * n_step * 3);
+    block_copy_out(deltas + row0 * 2, sl, rays_here * n_step * 2);
+}
+
 // raymarching.cu:1021-1104
 __global__ void __launch_bounds__(128) composite_rays_kernel(const uint32_t n_alive, const uint32_t n_step, const int* __restrict__ rays_alive,
                                                              float* __restrict__ rays_t, const float* __restrict__ sigmas, const float* __restrict__ rgbs,
@@ -635,6 +708,12 @@ extern "C" int ntx_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays
     uint32_t threads = n_alive;
     if (zero_fill) threads = max(threads, M_padded - n_alive * n_step);
     if (threads == 0) return NTX_OK;
+    if (zero_fill && n_step >= 1 && n_step <= kMarchMaxStagedSteps && ((reinterpret_cast<uintptr_t>(xyzs) | reinterpret_cast<uintptr_t>(dirs) | reinterpret_cast<uintptr_t>(deltas)) & 15) == 0) {
+        const size_t smem = (size_t)kMarchThreads * n_step * 8 * sizeof(float);
+        march_rays_staged_kernel<<<ceil_div<uint32_t>(threads, kMarchThreads), kMarchThreads, smem, ST(stream)>>>(
+            n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs, dirs, deltas, perturb, M_padded);
+        return check_launch("march_rays");
+    }
     march_rays_kernel<<<ceil_div<uint32_t>(threads, 128), 128, 0, ST(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid,
                                                                                nears, fars, xyzs, dirs, deltas, perturb, zero_fill, M_padded);
     return check_launch("march_rays");
