@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libntx.so")
-SOURCES = ["api.cu", "grid.cu", "sh.cu", "raymarch.cu", "mlp.cu", "field.cu"]
+SOURCES = ["api.cu", "grid.cu", "sh.cu", "raymarch.cu", "mlp.cu", "mlp_bwd.cu", "field.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr", "-Xptxas", "-v",

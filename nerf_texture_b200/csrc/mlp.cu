@@ -186,7 +186,9 @@ static int mlp_forward_dispatch(const void* inputs, const void* weights, uint32_
     NTX_REQUIRE(!train || forward_buffer, NTX_ERR_INVALID_ARGUMENT, "ffmlp_forward: forward_buffer required");
     NTX_REQUIRE(input_dim > 0 && input_dim % 16 == 0, NTX_ERR_INVALID_ARGUMENT, "FFMLP input_dim should be 16 * m (m > 0), but got %u", input_dim);
     NTX_REQUIRE(output_dim == 16, NTX_ERR_UNSUPPORTED, "FFMLP current only supports output dim <= 16 (padded to 16), but got %u", output_dim);
-    NTX_REQUIRE(num_layers >= 2, NTX_ERR_INVALID_ARGUMENT, "FFMLP num_layers should be larger than 2 (3 matmuls), but got %u", num_layers);
+    // FFMLP (ffmlp.py:115) asserts num_layers >= 2; the kernel itself also handles one hidden layer (2 matmuls), which the
+    // tinycudann shim needs for n_hidden_layers == 1 networks (network_curvedfield.py:173)
+    NTX_REQUIRE(num_layers >= 1, NTX_ERR_INVALID_ARGUMENT, "FFMLP num_layers must be positive, but got %u", num_layers);
     NTX_REQUIRE(((uintptr_t)inputs & 15) == 0 && ((uintptr_t)weights & 15) == 0 && ((uintptr_t)outputs & 15) == 0, NTX_ERR_INVALID_ARGUMENT,
                 "ffmlp: inputs / weights / outputs must be 16-byte aligned");
     if (B == 0) return NTX_OK;

@@ -124,6 +124,22 @@ __device__ __forceinline__ bool probe(const Ray& r, const MarchParams& p, float&
     return false;
 }
 
+// The address part of probe() only: sample position, step length and the occupancy bit index at parameter t (same
+// expressions as probe(), so the values are bit-identical).  Used to issue several occupancy loads back to back.
+__device__ __forceinline__ uint32_t locate(const Ray& r, const MarchParams& p, const float t, float& x, float& y, float& z, float& dt) {
+    x = clampf(r.ox + t * r.dx, -p.bound, p.bound);
+    y = clampf(r.oy + t * r.dy, -p.bound, p.bound);
+    z = clampf(r.oz + t * r.dz, -p.bound, p.bound);
+    dt = clampf(t * p.dt_gamma, p.dt_min, p.dt_max);
+    const int level = max(mip_from_pos(x, y, z, p.C), mip_from_dt(dt, p.H, p.C));
+    const float mip_bound = fminf((float)(1 << level), p.bound);
+    const float mip_rbound = 1 / mip_bound;
+    const int nx = clampf(0.5 * (x * mip_rbound + 1) * p.H, 0.0f, (float)(p.H - 1));
+    const int ny = clampf(0.5 * (y * mip_rbound + 1) * p.H, 0.0f, (float)(p.H - 1));
+    const int nz = clampf(0.5 * (z * mip_rbound + 1) * p.H, 0.0f, (float)(p.H - 1));
+    return level * p.H * p.H * p.H + morton3D_1(nx, ny, nz);
+}
+
 // ---------------------------------------------------------------------------------------------------- ordered grid-wide scan
 // Workspace layout: u32 ticket, u32 done, then one u64 status word per block:
 //   bits 63..62: 0 = nothing yet, 1 = block aggregate, 2 = inclusive prefix;  bits 61..0: value.
@@ -528,6 +544,41 @@ __global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
         }
         float last_t = t, x, y, z, dt;
         uint32_t step = 0;
+        {
+            // Speculation: inside the object every probe is occupied, so the next n_step sample positions are t, t+dt, ...
+            // (the same float additions the sequential marcher performs).  Issue all their occupancy loads at once instead
+            // of one dependent load per step, then accept the longest all-occupied prefix; the first empty voxel falls back
+            // to the sequential loop below at exactly the state the reference would be in.
+            float tq[kMarchMaxStagedSteps];
+            uint32_t bitidx[kMarchMaxStagedSteps], byte[kMarchMaxStagedSteps];
+            float tcur = t;
+            uint32_t nspec = 0;
+#pragma unroll
+            for (uint32_t s = 0; s < kMarchMaxStagedSteps; s++) {
+                tq[s] = tcur; bitidx[s] = 0; byte[s] = 0;
+                if (s < n_step && tcur < far) {
+                    const uint32_t index = locate(r, p, tcur, x, y, z, dt);
+                    bitidx[s] = index & 7u;
+                    byte[s] = p.grid[index >> 3];
+                    tcur += dt;
+                    nspec = s + 1;
+                }
+            }
+#pragma unroll
+            for (uint32_t s = 0; s < kMarchMaxStagedSteps; s++) {
+                if (s < nspec && step == s) {                     // step == s: all earlier speculated probes were occupied
+                    if (byte[s] & (1u << bitidx[s])) {
+                        locate(r, p, tq[s], x, y, z, dt);
+                        px[0] = x; px[1] = y; px[2] = z;
+                        pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+                        t = tq[s] + dt;
+                        pl[0] = dt; pl[1] = t - last_t;
+                        last_t = t;
+                        px += 3; pd += 3; pl += 2; step++;
+                    }
+                }
+            }
+        }
         while (t < far && step < n_step) {
             if (probe(r, p, t, x, y, z, dt)) {
                 px[0] = x; px[1] = y; px[2] = z;
