@@ -261,8 +261,14 @@ def main():
         live = sum(int(c.item()) for _, _, c, _ in prof)
         rows = sum(m for _, _, _, m in prof)
         achieved = live * FIELD_BYTES_PER_SAMPLE / kt / 1e9
+        traffic = None   # DRAM bytes of one in-frame launch from the committed `ncu --set full` capture (profiles/)
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_field_kernel_traffic.json")))["dram_bytes_per_launch_in_frame"]
+        except Exception:
+            pass
         line["roofline"] = {"bound": "hbm", "kernel": "ngp_field_kernel (hash-grid gather + sigma MLP + SH + colour MLP)", "achieved": achieved,
-                            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": live * FIELD_BYTES_PER_SAMPLE / max(len(prof), 1),
                             "algorithmic_bytes_per_sample": FIELD_BYTES_PER_SAMPLE, "launches": len(prof), "avg_launch_us": kt / max(len(prof), 1) * 1e6,
                             "live_samples": live, "rows": rows, "kernel_share_of_step": kt * 1e3 / ms,
                             "msamples_per_s_in_kernel": live / kt / 1e6,
