@@ -133,7 +133,13 @@ int ntx_composite_rays_train_backward(const float* grad_weights_sum, const float
 int ntx_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, const float* rays_t, const float* rays_o,
                    const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
                    const uint8_t* grid, const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
-                   uint32_t perturb, int zero_fill, uint32_t M_padded, ntx_stream_t stream);
+                   uint32_t perturb, int zero_fill, uint32_t M_padded, const uint8_t* occupancy_mip /* nullable */, ntx_stream_t stream);
+/* Optional accelerator of march_rays: a conservative (dilated) 8x8x8-cell mip of the occupancy bit-field.  With it the marcher
+ * stops walking a ray through empty space as soon as no occupied voxel can be reached any more; the emitted samples are
+ * unchanged (such a ray emits nothing further and is marked dead by composite_rays whatever t it stops at).
+ * mip: ntx_occupancy_mip_bytes(C,H) bytes; rebuild whenever the bit-field changes.  H must be a power of two >= 16. */
+size_t ntx_occupancy_mip_bytes(uint32_t C, uint32_t H);
+int ntx_build_occupancy_mip(const uint8_t* grid, uint32_t C, uint32_t H, uint8_t* mip, ntx_stream_t stream);
 int ntx_composite_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, float* rays_t, const float* sigmas,
                        const float* rgbs, const float* deltas, float* weights_sum, float* depth, float* image,
                        ntx_stream_t stream);

@@ -37,7 +37,8 @@ _SIGS = {
     "ntx_march_rays_train": [_vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _vp, _vp],
     "ntx_composite_rays_train_forward": [_vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp],
     "ntx_composite_rays_train_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp],
-    "ntx_march_rays": [_u32, _u32, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _int, _u32, _vp],
+    "ntx_march_rays": [_u32, _u32, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _int, _u32, _vp, _vp],
+    "ntx_build_occupancy_mip": [_vp, _u32, _u32, _vp, _vp],
     "ntx_composite_rays": [_u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ntx_compact_rays": [_u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ntx_ngp_field_forward": [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _u32, _f32, _u32, _int, _vp, _vp, _f32, _vp, _vp, _vp],
@@ -45,6 +46,7 @@ _SIGS = {
 _SIZE_FNS = {
     "ntx_march_rays_train_workspace_bytes": [_u32],
     "ntx_compact_rays_workspace_bytes": [_u32],
+    "ntx_occupancy_mip_bytes": [_u32, _u32],
     "ntx_ffmlp_backward_workspace_bytes": [_u32, _u32, _u32, _u32],
 }
 

@@ -103,6 +103,7 @@ class _packbits(Function):
         if bitfield is None:
             bitfield = torch.empty(N, dtype=torch.uint8, device=grid.device)
         L.call("ntx_packbits", L.ptr(grid), N, float(thresh), L.ptr(bitfield), L.stream())
+        _mip_cache.pop(bitfield.data_ptr(), None)   # the bit-field changed behind torch's version counter
         return bitfield
 
 
@@ -218,6 +219,24 @@ composite_rays_train = _composite_rays_train.apply
 
 
 # ---------------------------------------------------------------------------------------------------- inference
+_mip_cache = {}
+
+
+def _occupancy_mip(bitfield, C, H):
+    """conservative occupancy mip of `bitfield` (see ntx_build_occupancy_mip), cached per (storage, version): rebuilt whenever torch
+    has seen the bit-field change; our own packbits() (which writes through a raw pointer) invalidates it explicitly"""
+    if H < 16 or (H & (H - 1)) != 0 or (bitfield.data_ptr() & 15) != 0:
+        return None
+    key = (bitfield.data_ptr(), bitfield._version, C, H)
+    hit = _mip_cache.get(bitfield.data_ptr())
+    if hit is None or hit[0] != key:
+        mip = torch.empty(L.lib().ntx_occupancy_mip_bytes(C, H), dtype=torch.uint8, device=bitfield.device)
+        L.call("ntx_build_occupancy_mip", L.ptr(bitfield), C, H, L.ptr(mip), L.stream())
+        _mip_cache[bitfield.data_ptr()] = (key, mip)
+        hit = _mip_cache[bitfield.data_ptr()]
+    return hit[1].data_ptr()
+
+
 class _march_rays(Function):
     @staticmethod
     @_fwd32
@@ -235,7 +254,7 @@ class _march_rays(Function):
         deltas = torch.empty(M, 2, dtype=rays_o.dtype, device=dev)
         L.call("ntx_march_rays", int(n_alive), int(n_step), L.ptr(rays_alive), L.ptr(rays_t), L.ptr(rays_o), L.ptr(rays_d), float(bound),
                float(dt_gamma), int(max_steps), int(C), int(H), L.ptr(density_bitfield), L.ptr(near), L.ptr(far), L.ptr(xyzs), L.ptr(dirs),
-               L.ptr(deltas), int(perturb), 1, M, L.stream())
+               L.ptr(deltas), int(perturb), 1, M, _occupancy_mip(density_bitfield, int(C), int(H)), L.stream())
         return xyzs, dirs, deltas
 
 

@@ -140,6 +140,72 @@ __device__ __forceinline__ uint32_t locate(const Ray& r, const MarchParams& p, c
     return level * p.H * p.H * p.H + morton3D_1(nx, ny, nz);
 }
 
+// ---------------------------------------------------------------------------------------------------- conservative occupancy mip
+// A ray that has left the object keeps marching to `far` voxel by voxel in the reference (one dependent probe per empty voxel);
+// it emits nothing on the way, and because it then comes back with fewer than n_step samples composite_rays marks it dead, so
+// the exact t it stops at is unobservable.  The mip lets the marcher prove "no occupied voxel can be probed on [t, far)" and stop.
+//   coarse bit (cascade k, cell c) = OR of the 8x8x8 fine voxels of that cell = OR of 64 consecutive bytes (Morton order),
+//   then dilated by one coarse cell in every direction, so that testing sample points spaced half a coarse cell apart is
+//   conservative for every point in between (and for the marcher's clamping at cascade borders).
+// Buffer: [dilated: C*n/8 bytes][raw: C*n/8 bytes], n = (H/8)^3 (Morton order).
+__global__ void __launch_bounds__(128) occupancy_mip_raw_kernel(const uint8_t* __restrict__ grid, const uint32_t cells_total, uint8_t* __restrict__ raw) {
+    const uint32_t byte = blockIdx.x * blockDim.x + threadIdx.x;       // one output byte = 8 coarse cells = 512 fine bytes
+    if (byte >= cells_total / 8) return;
+    uint32_t bits = 0;
+#pragma unroll
+    for (uint32_t c = 0; c < 8; c++) {
+        const uint4* src = reinterpret_cast<const uint4*>(grid + ((size_t)byte * 8 + c) * 64);
+        uint32_t any = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const uint4 v = src[q]; any |= v.x | v.y | v.z | v.w; }
+        bits |= (any ? 1u : 0u) << c;
+    }
+    raw[byte] = (uint8_t)bits;
+}
+__global__ void __launch_bounds__(128) occupancy_mip_dilate_kernel(const uint8_t* __restrict__ raw, const uint32_t C, const uint32_t Hc, uint8_t* __restrict__ dil) {
+    const uint32_t n = Hc * Hc * Hc;
+    const uint32_t byte = blockIdx.x * blockDim.x + threadIdx.x;
+    if (byte >= C * n / 8) return;
+    const uint32_t k = (byte * 8) / n;
+    uint32_t bits = 0;
+    for (uint32_t c = 0; c < 8; c++) {
+        const uint32_t m = byte * 8 + c - k * n;
+        const int x = morton3D_invert_1(m), y = morton3D_invert_1(m >> 1), z = morton3D_invert_1(m >> 2);
+        uint32_t any = 0;
+        for (int dz = -1; dz <= 1; dz++)
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    const int xx = x + dx, yy = y + dy, zz = z + dz;
+                    if (xx < 0 || yy < 0 || zz < 0 || xx >= (int)Hc || yy >= (int)Hc || zz >= (int)Hc) continue;
+                    const uint32_t idx = k * n + morton3D_1(xx, yy, zz);
+                    any |= raw[idx >> 3] & (1u << (idx & 7u));
+                }
+        bits |= (any ? 1u : 0u) << c;
+    }
+    dil[byte] = (uint8_t)bits;
+}
+
+// true if an occupied voxel MAY be probed by the marcher anywhere on the ray segment [t, far)
+__device__ __forceinline__ bool maybe_occupied_ahead(const Ray& r, const MarchParams& p, const uint8_t* __restrict__ coarse, float t, const float far) {
+    const uint32_t Hc = p.H >> 3, n = Hc * Hc * Hc;
+    const float inv_speed = 1.0f / fmaxf(fmaxf(fabsf(r.dx), fabsf(r.dy)), fmaxf(fabsf(r.dz), 1e-20f));
+    while (t < far) {
+        const float x = r.ox + t * r.dx, y = r.oy + t * r.dy, z = r.oz + t * r.dz;
+        for (uint32_t k = 0; k < p.C; k++) {
+            const float mb = fminf((float)(1 << k), p.bound), s = 0.5f * (float)Hc / mb;
+            const int cx = min(max((int)floorf((clampf(x, -mb, mb) + mb) * s), 0), (int)Hc - 1);
+            const int cy = min(max((int)floorf((clampf(y, -mb, mb) + mb) * s), 0), (int)Hc - 1);
+            const int cz = min(max((int)floorf((clampf(z, -mb, mb) + mb) * s), 0), (int)Hc - 1);
+            const uint32_t idx = k * n + morton3D_1(cx, cy, cz);
+            if (coarse[idx >> 3] & (1u << (idx & 7u))) return true;
+        }
+        // advance half a coarse cell (of the cascade this point lies in) along the fastest axis
+        const int lp = mip_from_pos(clampf(x, -p.bound, p.bound), clampf(y, -p.bound, p.bound), clampf(z, -p.bound, p.bound), p.C);
+        t += (8.0f * fminf((float)(1 << lp), p.bound) / (float)p.H) * inv_speed;
+    }
+    return false;
+}
+
 // ---------------------------------------------------------------------------------------------------- ordered grid-wide scan
 // Workspace layout: u32 ticket, u32 done, then one u64 status word per block:
 //   bits 63..62: 0 = nothing yet, 1 = block aggregate, 2 = inclusive prefix;  bits 61..0: value.
@@ -512,7 +578,7 @@ __global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
     const uint32_t n_alive, const uint32_t n_step, const int* __restrict__ rays_alive, const float* __restrict__ rays_t, const float* __restrict__ rays_o,
     const float* __restrict__ rays_d, const float bound, const float dt_gamma, const uint32_t max_steps, const uint32_t C, const uint32_t H,
     const uint8_t* __restrict__ grid, const float* __restrict__ nears, const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs,
-    float* __restrict__ deltas, const uint32_t perturb, const uint32_t M_padded) {
+    float* __restrict__ deltas, const uint32_t perturb, const uint32_t M_padded, const uint8_t* __restrict__ coarse) {
     extern __shared__ __align__(16) float stage[];          // [128*n_step*3] xyz | [128*n_step*3] dir | [128*n_step*2] delta
     float* sx = stage;
     float* sd = stage + kMarchThreads * n_step * 3;
@@ -579,6 +645,7 @@ __global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
                 }
             }
         }
+        uint32_t empties = 0;
         while (t < far && step < n_step) {
             if (probe(r, p, t, x, y, z, dt)) {
                 px[0] = x; px[1] = y; px[2] = z;
@@ -587,6 +654,10 @@ __global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
                 pl[0] = dt; pl[1] = t - last_t;
                 last_t = t;
                 px += 3; pd += 3; pl += 2; step++;
+            } else if (coarse && ((empties++ & 7u) == 0u)) {
+                // in empty space: if nothing occupied can be reached any more, this ray emits no further sample and is dead
+                // after composite_rays whatever t it stops at — skip the voxel-by-voxel walk to `far`
+                if (!maybe_occupied_ahead(r, p, coarse, t, far)) break;
             }
         }
         for (; step < n_step; step++) {                      // unused slots: zero (delta == 0 is composite_rays' stop sentinel)
@@ -752,8 +823,9 @@ extern "C" int ntx_composite_rays_train_backward(const float* grad_weights_sum, 
 
 extern "C" int ntx_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, const float* rays_t, const float* rays_o, const float* rays_d, float bound,
                               float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars, float* xyzs,
-                              float* dirs, float* deltas, uint32_t perturb, int zero_fill, uint32_t M_padded, ntx_stream_t stream) {
+                              float* dirs, float* deltas, uint32_t perturb, int zero_fill, uint32_t M_padded, const uint8_t* occupancy_mip, ntx_stream_t stream) {
     NTX_REQUIRE(rays_alive && rays_t && rays_o && rays_d && grid && nears && fars && xyzs && dirs && deltas, NTX_ERR_INVALID_ARGUMENT, "march_rays: null pointer");
+    if (occupancy_mip && ((H & (H - 1)) != 0 || H < 8)) occupancy_mip = nullptr;   // the mip needs a power-of-two grid
     NTX_REQUIRE(C >= 1 && C <= 16 && H >= 1 && H <= 1024 && max_steps >= 1, NTX_ERR_INVALID_ARGUMENT, "march_rays: bad C/H/max_steps");
     NTX_REQUIRE(!zero_fill || M_padded >= n_alive * n_step, NTX_ERR_INVALID_ARGUMENT, "march_rays: M_padded smaller than n_alive*n_step");
     uint32_t threads = n_alive;
@@ -762,12 +834,26 @@ extern "C" int ntx_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays
     if (zero_fill && n_step >= 1 && n_step <= kMarchMaxStagedSteps && ((reinterpret_cast<uintptr_t>(xyzs) | reinterpret_cast<uintptr_t>(dirs) | reinterpret_cast<uintptr_t>(deltas)) & 15) == 0) {
         const size_t smem = (size_t)kMarchThreads * n_step * 8 * sizeof(float);
         march_rays_staged_kernel<<<ceil_div<uint32_t>(threads, kMarchThreads), kMarchThreads, smem, ST(stream)>>>(
-            n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs, dirs, deltas, perturb, M_padded);
+            n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs, dirs, deltas, perturb, M_padded,
+            occupancy_mip);
         return check_launch("march_rays");
     }
     march_rays_kernel<<<ceil_div<uint32_t>(threads, 128), 128, 0, ST(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid,
                                                                                nears, fars, xyzs, dirs, deltas, perturb, zero_fill, M_padded);
     return check_launch("march_rays");
+}
+
+extern "C" size_t ntx_occupancy_mip_bytes(uint32_t C, uint32_t H) { return 2 * (size_t)C * (H / 8) * (H / 8) * (H / 8) / 8; }
+
+extern "C" int ntx_build_occupancy_mip(const uint8_t* grid, uint32_t C, uint32_t H, uint8_t* mip, ntx_stream_t stream) {
+    NTX_REQUIRE(grid && mip, NTX_ERR_INVALID_ARGUMENT, "build_occupancy_mip: null pointer");
+    NTX_REQUIRE(C >= 1 && C <= 16 && H >= 16 && H <= 1024 && (H & (H - 1)) == 0, NTX_ERR_UNSUPPORTED, "build_occupancy_mip: H must be a power of two in [16, 1024]");
+    NTX_REQUIRE((reinterpret_cast<uintptr_t>(grid) & 15) == 0, NTX_ERR_INVALID_ARGUMENT, "build_occupancy_mip: bit-field must be 16-byte aligned");
+    const uint32_t Hc = H / 8, cells = C * Hc * Hc * Hc;
+    uint8_t* raw = mip + cells / 8;
+    occupancy_mip_raw_kernel<<<ceil_div<uint32_t>(cells / 8, 128), 128, 0, ST(stream)>>>(grid, cells, raw);
+    occupancy_mip_dilate_kernel<<<ceil_div<uint32_t>(cells / 8, 128), 128, 0, ST(stream)>>>(raw, C, Hc, mip);
+    return check_launch("build_occupancy_mip");
 }
 
 extern "C" int ntx_composite_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, float* rays_t, const float* sigmas, const float* rgbs, const float* deltas,

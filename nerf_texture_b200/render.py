@@ -76,7 +76,7 @@ class NGPField:
 
 
 def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aabb=None, min_near=0.2, dt_gamma=0.0, max_steps=1024, bg_color=1.0,
-                perturb=0, count_samples=False, profile=None):
+                perturb=0, count_samples=False, profile=None, use_mip=True):
     """Inference branch of NeRFRenderer.run_cuda (renderer.py:436-489).  rays_o/d [N,3] fp32 CUDA.
     Returns dict(image [N,3], depth [N], weights_sum [N], iterations, n_samples (if count_samples)).
     profile: optional list; gets one (start_event, stop_event, live_sample_count_tensor) per field-kernel launch."""
@@ -108,6 +108,10 @@ def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aab
     rgbs = torch.empty(Mmax, 3, dtype=torch.float32, device=dev)
     ws = L.workspace("compact", L.lib().ntx_compact_rays_workspace_bytes(N), dev)
     n_samples = torch.zeros(1, dtype=torch.int64, device=dev) if count_samples else None
+    mip = None
+    if use_mip and grid_size >= 16 and (grid_size & (grid_size - 1)) == 0:
+        mip = torch.empty(L.lib().ntx_occupancy_mip_bytes(int(cascade), int(grid_size)), dtype=torch.uint8, device=dev)
+        L.call("ntx_build_occupancy_mip", L.ptr(density_bitfield), int(cascade), int(grid_size), L.ptr(mip), st)
 
     n_alive, step, i = N, 0, 0
     while step < max_steps:
@@ -124,7 +128,7 @@ def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aab
         M += 128 - (M % 128)
         L.call("ntx_march_rays", n_alive, n_step, L.ptr(rays_alive[cur]), L.ptr(rays_t[cur]), L.ptr(rays_o), L.ptr(rays_d), bound, float(dt_gamma),
                int(max_steps), int(cascade), int(grid_size), L.ptr(density_bitfield), L.ptr(nears), L.ptr(fars), L.ptr(xyzs), L.ptr(dirs), L.ptr(deltas),
-               int(perturb), 1, M, st)
+               int(perturb), 1, M, None if mip is None else L.ptr(mip), st)
         if profile is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()

@@ -181,8 +181,8 @@ def test_composite_rays_train_forward_backward():
     np.testing.assert_allclose(gc.cpu().numpy(), ogc, rtol=2e-5, atol=2e-6)
 
 
-@pytest.mark.parametrize("perturb", [0, 3])
-def test_inference_loop_march_composite_compact(perturb):
+@pytest.mark.parametrize("perturb,use_mip", [(0, False), (3, False), (0, True), (3, True)])
+def test_inference_loop_march_composite_compact(perturb, use_mip):
     """the body of renderer.py:459-485 for a few iterations, libntx vs oracle (exact) and vs reference CUDA (as sets)"""
     L_ = ntx()
     O, o, d, grid, bits, aabb, nears, fars = _scene(Himg=40, Wimg=40)
@@ -201,6 +201,9 @@ def test_inference_loop_march_composite_compact(perturb):
     w_alive, w_t = np.arange(N, dtype=np.int32), nears.copy()
     w_ws, w_dp, w_im = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros((N, 3), np.float32)
 
+    mip = torch.empty(L_.lib().ntx_occupancy_mip_bytes(1, 128), dtype=torch.uint8, device=DEV)
+    L_.call("ntx_build_occupancy_mip", bt.data_ptr(), 1, 128, mip.data_ptr(), L_.stream())
+    mip_ptr = mip.data_ptr() if use_mip else None
     n_alive, i, step = N, 0, 0
     while step < 64:
         if step > 0:
@@ -230,7 +233,7 @@ def test_inference_loop_march_composite_compact(perturb):
         Mp = n_alive * n_step; Mp += 128 - (Mp % 128)
         gx = torch.full((Mp, 3), float("nan"), device=DEV); gd = torch.full((Mp, 3), float("nan"), device=DEV); gl = torch.full((Mp, 2), float("nan"), device=DEV)
         L_.call("ntx_march_rays", n_alive, n_step, g_alive[i % 2].data_ptr(), g_t[i % 2].data_ptr(), ot.data_ptr(), dt.data_ptr(), 1.0, 0.0, 1024, 1, 128,
-                bt.data_ptr(), nt.data_ptr(), ft.data_ptr(), gx.data_ptr(), gd.data_ptr(), gl.data_ptr(), perturb, 1, Mp, L_.stream())
+                bt.data_ptr(), nt.data_ptr(), ft.data_ptr(), gx.data_ptr(), gd.data_ptr(), gl.data_ptr(), perturb, 1, Mp, mip_ptr, L_.stream())
         rx, rd, rl = torch.zeros(Mp, 3, device=DEV), torch.zeros(Mp, 3, device=DEV), torch.zeros(Mp, 2, device=DEV)
         m.march_rays(n_alive, n_step, r_alive[i % 2], r_t[i % 2], ot, dt, 1.0, 0.0, 1024, 1, 128, bt, nt, ft, rx, rd, rl, perturb)
         wx, wd, wl = O.march_rays(n_alive, n_step, w_alive, w_t, o, d, 1.0, bits, 1, 128, nears, fars, align=128, perturb=perturb, max_steps=1024)
