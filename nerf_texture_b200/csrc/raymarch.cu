@@ -82,6 +82,11 @@ struct MarchParams {
     float bound, dt_gamma, dt_min, dt_max, rH;
     uint32_t C, H;
     const uint8_t* __restrict__ grid;
+    // single cascade + power-of-two grid (NeRF-Texture: bound 1, H 128): the cascade level is always 0 and the voxel index can be
+    // computed in fp32 with bit-identical results (multiplying by 0.5*H is an exact scaling, so the reference's detour through
+    // double precision in `0.5 * (x * rbound + 1) * H` changes nothing)
+    bool fast;
+    float mb0, rb0, halfH;
 };
 
 __device__ __forceinline__ MarchParams make_march_params(float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid) {
@@ -91,6 +96,10 @@ __device__ __forceinline__ MarchParams make_march_params(float bound, float dt_g
     p.dt_max = 2 * kSqrt3 * (1 << (C - 1)) / H;      // :347
     p.rH = 1 / (float)H;
     p.C = C; p.H = H; p.grid = grid;
+    p.fast = (C == 1) && ((H & (H - 1)) == 0);
+    p.mb0 = fminf(1.0f, bound);
+    p.rb0 = 1 / p.mb0;
+    p.halfH = 0.5f * (float)H;
     return p;
 }
 __device__ __forceinline__ Ray load_ray(const float* __restrict__ o, const float* __restrict__ d) {
@@ -107,6 +116,19 @@ __device__ __forceinline__ bool probe(const Ray& r, const MarchParams& p, float&
     y = clampf(r.oy + t * r.dy, -p.bound, p.bound);
     z = clampf(r.oz + t * r.dz, -p.bound, p.bound);
     dt = clampf(t * p.dt_gamma, p.dt_min, p.dt_max);
+    if (p.fast) {   // level == 0, fp32 index math (see MarchParams::fast)
+        const int nx = clampf((x * p.rb0 + 1) * p.halfH, 0.0f, (float)(p.H - 1));
+        const int ny = clampf((y * p.rb0 + 1) * p.halfH, 0.0f, (float)(p.H - 1));
+        const int nz = clampf((z * p.rb0 + 1) * p.halfH, 0.0f, (float)(p.H - 1));
+        const uint32_t index = morton3D_1(nx, ny, nz);
+        if (p.grid[index >> 3] & (1u << (index & 7u))) return true;
+        const float tx = (((nx + 0.5f + 0.5f * signf1(r.dx)) * p.rH * 2 - 1) * p.mb0 - x) * r.rdx;
+        const float ty = (((ny + 0.5f + 0.5f * signf1(r.dy)) * p.rH * 2 - 1) * p.mb0 - y) * r.rdy;
+        const float tz = (((nz + 0.5f + 0.5f * signf1(r.dz)) * p.rH * 2 - 1) * p.mb0 - z) * r.rdz;
+        const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+        do { t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max); } while (t < tt);
+        return false;
+    }
     const int level = max(mip_from_pos(x, y, z, p.C), mip_from_dt(dt, p.H, p.C));
     const float mip_bound = fminf((float)(1 << level), p.bound);
     const float mip_rbound = 1 / mip_bound;
@@ -131,6 +153,12 @@ __device__ __forceinline__ uint32_t locate(const Ray& r, const MarchParams& p, c
     y = clampf(r.oy + t * r.dy, -p.bound, p.bound);
     z = clampf(r.oz + t * r.dz, -p.bound, p.bound);
     dt = clampf(t * p.dt_gamma, p.dt_min, p.dt_max);
+    if (p.fast) {
+        const int nx = clampf((x * p.rb0 + 1) * p.halfH, 0.0f, (float)(p.H - 1));
+        const int ny = clampf((y * p.rb0 + 1) * p.halfH, 0.0f, (float)(p.H - 1));
+        const int nz = clampf((z * p.rb0 + 1) * p.halfH, 0.0f, (float)(p.H - 1));
+        return morton3D_1(nx, ny, nz);
+    }
     const int level = max(mip_from_pos(x, y, z, p.C), mip_from_dt(dt, p.H, p.C));
     const float mip_bound = fminf((float)(1 << level), p.bound);
     const float mip_rbound = 1 / mip_bound;
@@ -144,23 +172,42 @@ __device__ __forceinline__ uint32_t locate(const Ray& r, const MarchParams& p, c
 // A ray that has left the object keeps marching to `far` voxel by voxel in the reference (one dependent probe per empty voxel);
 // it emits nothing on the way, and because it then comes back with fewer than n_step samples composite_rays marks it dead, so
 // the exact t it stops at is unobservable.  The mip lets the marcher prove "no occupied voxel can be probed on [t, far)" and stop.
-//   coarse bit (cascade k, cell c) = OR of the 8x8x8 fine voxels of that cell = OR of 64 consecutive bytes (Morton order),
+//   coarse bit (cascade k, cell c) = OR of the 4x4x4 fine voxels of that cell = OR of 8 consecutive bytes (Morton order),
 //   then dilated by one coarse cell in every direction, so that testing sample points spaced half a coarse cell apart is
 //   conservative for every point in between (and for the marcher's clamping at cascade borders).
-// Buffer: [dilated: C*n/8 bytes][raw: C*n/8 bytes], n = (H/8)^3 (Morton order).
-__global__ void __launch_bounds__(128) occupancy_mip_raw_kernel(const uint8_t* __restrict__ grid, const uint32_t cells_total, uint8_t* __restrict__ raw) {
-    const uint32_t byte = blockIdx.x * blockDim.x + threadIdx.x;       // one output byte = 8 coarse cells = 512 fine bytes
+// Buffer: [header 512 B: int bbox[C][6] of the occupied coarse cells][dilated: C*n/8 bytes][raw: C*n/8 bytes], n = (H/4)^3 (Morton order).
+constexpr uint32_t kMipShift = 2;                       // coarse cell = 4 fine voxels per side
+constexpr uint32_t kMipCell = 1u << kMipShift;
+constexpr uint32_t kMipHeaderBytes = 512;               // 16 cascades x 6 ints
+
+__global__ void occupancy_mip_init_kernel(int* __restrict__ bbox, const uint32_t C) {
+    const uint32_t i = threadIdx.x;
+    if (i < C * 6) bbox[i] = (i % 6 < 3) ? 0x7fffffff : -0x7fffffff;   // min x,y,z | max x,y,z
+}
+__global__ void __launch_bounds__(128) occupancy_mip_raw_kernel(const uint8_t* __restrict__ grid, const uint32_t cells_total, const uint32_t cells_per_cascade,
+                                                                uint8_t* __restrict__ raw, int* __restrict__ bbox) {
+    const uint32_t byte = blockIdx.x * blockDim.x + threadIdx.x;       // one output byte = 8 coarse cells = 8 x 8 fine bytes
     if (byte >= cells_total / 8) return;
+    const uint4* src = reinterpret_cast<const uint4*>(grid + (size_t)byte * 64);
     uint32_t bits = 0;
 #pragma unroll
-    for (uint32_t c = 0; c < 8; c++) {
-        const uint4* src = reinterpret_cast<const uint4*>(grid + ((size_t)byte * 8 + c) * 64);
-        uint32_t any = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) { const uint4 v = src[q]; any |= v.x | v.y | v.z | v.w; }
-        bits |= (any ? 1u : 0u) << c;
+    for (int q = 0; q < 4; q++) {
+        const uint4 v = src[q];
+        bits |= ((v.x | v.y) ? 1u : 0u) << (2 * q);
+        bits |= ((v.z | v.w) ? 1u : 0u) << (2 * q + 1);
     }
     raw[byte] = (uint8_t)bits;
+    if (bits) {
+        const uint32_t k = (byte * 8) / cells_per_cascade;
+        int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {-1, -1, -1};
+        for (uint32_t c = 0; c < 8; c++)
+            if (bits & (1u << c)) {
+                const uint32_t m = byte * 8 + c - k * cells_per_cascade;
+                const int q[3] = {(int)morton3D_invert_1(m), (int)morton3D_invert_1(m >> 1), (int)morton3D_invert_1(m >> 2)};
+                for (int a = 0; a < 3; a++) { lo[a] = min(lo[a], q[a]); hi[a] = max(hi[a], q[a]); }
+            }
+        for (int a = 0; a < 3; a++) { atomicMin(&bbox[k * 6 + a], lo[a]); atomicMax(&bbox[k * 6 + 3 + a], hi[a]); }
+    }
 }
 __global__ void __launch_bounds__(128) occupancy_mip_dilate_kernel(const uint8_t* __restrict__ raw, const uint32_t C, const uint32_t Hc, uint8_t* __restrict__ dil) {
     const uint32_t n = Hc * Hc * Hc;
@@ -185,10 +232,63 @@ __global__ void __launch_bounds__(128) occupancy_mip_dilate_kernel(const uint8_t
     dil[byte] = (uint8_t)bits;
 }
 
+// Parameter interval [*t_lo, *t_hi] of the ray inside the union of the per-cascade bounding boxes of occupied coarse cells, each
+// grown by one coarse cell (conservative w.r.t. clamping and rounding).  Returns false if the ray misses all of them: then no
+// occupied voxel can ever be probed on this ray.
+__device__ __forceinline__ bool clip_to_occupied(const Ray& r, const MarchParams& p, const uint8_t* __restrict__ mip, float& t_lo, float& t_hi) {
+    const int* bbox = reinterpret_cast<const int*>(mip);
+    const float Hc = (float)(p.H >> kMipShift);
+    bool any = false;
+    t_lo = 3.402823466e+38f; t_hi = -3.402823466e+38f;
+    for (uint32_t k = 0; k < p.C; k++) {
+        const int* b = bbox + k * 6;
+        if (b[0] > b[3]) continue;                                // cascade has no occupied cell
+        const float mb = fminf((float)(1 << k), p.bound), cell = 2.0f * mb / Hc;
+        float lo = -3.402823466e+38f, hi = 3.402823466e+38f;
+        const float o[3] = {r.ox, r.oy, r.oz}, rd[3] = {r.rdx, r.rdy, r.rdz}, d[3] = {r.dx, r.dy, r.dz};
+        bool miss = false;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            float wmin = ((float)(b[a] - 1)) * cell - mb, wmax = ((float)(b[3 + a] + 2)) * cell - mb;   // grown by one cell each side
+            if (k + 1 == p.C || (float)(1 << k) >= p.bound) { if (b[a] == 0) wmin = -3.402823466e+38f; if (b[3 + a] == (int)Hc - 1) wmax = 3.402823466e+38f; }  // outermost cascade: clamped points land in border cells
+            if (d[a] == 0.0f) { if (o[a] < wmin || o[a] > wmax) miss = true; }
+            else {
+                float t0 = (wmin - o[a]) * rd[a], t1 = (wmax - o[a]) * rd[a];
+                if (t0 > t1) { const float c = t0; t0 = t1; t1 = c; }
+                lo = fmaxf(lo, t0); hi = fminf(hi, t1);
+            }
+        }
+        if (miss || lo > hi) continue;
+        any = true;
+        t_lo = fminf(t_lo, lo); t_hi = fmaxf(t_hi, hi);
+    }
+    return any;
+}
+
 // true if an occupied voxel MAY be probed by the marcher anywhere on the ray segment [t, far)
-__device__ __forceinline__ bool maybe_occupied_ahead(const Ray& r, const MarchParams& p, const uint8_t* __restrict__ coarse, float t, const float far) {
-    const uint32_t Hc = p.H >> 3, n = Hc * Hc * Hc;
+__device__ __forceinline__ bool maybe_occupied_ahead(const Ray& r, const MarchParams& p, const uint8_t* __restrict__ mip, float t, const float far) {
+    const uint8_t* __restrict__ coarse = mip + kMipHeaderBytes;
+    const uint32_t Hc = p.H >> kMipShift, n = Hc * Hc * Hc;
     const float inv_speed = 1.0f / fmaxf(fmaxf(fabsf(r.dx), fabsf(r.dy)), fmaxf(fabsf(r.dz), 1e-20f));
+    if (p.C == 1) {
+        // single cascade: cell coordinates are affine in t; test 4 sample points per round so that their loads overlap
+        const float mb = p.mb0, s = 0.5f * (float)Hc / mb, top = (float)(Hc - 1);
+        const float ax = (r.ox + mb) * s, ay = (r.oy + mb) * s, az = (r.oz + mb) * s, bx = r.dx * s, by = r.dy * s, bz = r.dz * s;
+        const float dt = ((float)kMipCell * mb / (float)p.H) * inv_speed;
+        while (t < far) {
+            uint32_t hit = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float tj = t + (float)j * dt;
+                const int cx = (int)clampf(ax + tj * bx, 0.0f, top), cy = (int)clampf(ay + tj * by, 0.0f, top), cz = (int)clampf(az + tj * bz, 0.0f, top);
+                const uint32_t idx = morton3D_1(cx, cy, cz);
+                hit |= (tj < far) ? (coarse[idx >> 3] & (1u << (idx & 7u))) : 0u;
+            }
+            if (hit) return true;
+            t += 4.0f * dt;
+        }
+        return false;
+    }
     while (t < far) {
         const float x = r.ox + t * r.dx, y = r.oy + t * r.dy, z = r.oz + t * r.dz;
         for (uint32_t k = 0; k < p.C; k++) {
@@ -201,7 +301,7 @@ __device__ __forceinline__ bool maybe_occupied_ahead(const Ray& r, const MarchPa
         }
         // advance half a coarse cell (of the cascade this point lies in) along the fastest axis
         const int lp = mip_from_pos(clampf(x, -p.bound, p.bound), clampf(y, -p.bound, p.bound), clampf(z, -p.bound, p.bound), p.C);
-        t += (8.0f * fminf((float)(1 << lp), p.bound) / (float)p.H) * inv_speed;
+        t += ((float)kMipCell * fminf((float)(1 << lp), p.bound) / (float)p.H) * inv_speed;   // half of (kMipCell * 2*mb/H)
     }
     return false;
 }
@@ -602,11 +702,17 @@ __global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
         float* px = sx + threadIdx.x * n_step * 3;
         float* pd = sd + threadIdx.x * n_step * 3;
         float* pl = sl + threadIdx.x * n_step * 2;
-        const float far = fars[index];
+        float far = fars[index];
         if (perturb) {
             Pcg32 rng; rng.seed((uint64_t)perturb);   // raymarching.cu:1011
             rng.advance(n);
             t += p.dt_min * rng.next_float();
+        }
+        if (coarse) {
+            // beyond the (grown) bounding box of everything occupied no sample can be emitted: shorten the walk, or skip it
+            // altogether for rays that miss the box.  Samples in front of `far` are unaffected.
+            float b_lo, b_hi;
+            if (clip_to_occupied(r, p, coarse, b_lo, b_hi)) far = fminf(far, b_hi); else far = t;
         }
         float last_t = t, x, y, z, dt;
         uint32_t step = 0;
@@ -654,7 +760,7 @@ __global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
                 pl[0] = dt; pl[1] = t - last_t;
                 last_t = t;
                 px += 3; pd += 3; pl += 2; step++;
-            } else if (coarse && ((empties++ & 7u) == 0u)) {
+            } else if (coarse && ((empties++ & 3u) == 0u)) {
                 // in empty space: if nothing occupied can be reached any more, this ray emits no further sample and is dead
                 // after composite_rays whatever t it stops at — skip the voxel-by-voxel walk to `far`
                 if (!maybe_occupied_ahead(r, p, coarse, t, far)) break;
@@ -843,16 +949,18 @@ extern "C" int ntx_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays
     return check_launch("march_rays");
 }
 
-extern "C" size_t ntx_occupancy_mip_bytes(uint32_t C, uint32_t H) { return 2 * (size_t)C * (H / 8) * (H / 8) * (H / 8) / 8; }
+extern "C" size_t ntx_occupancy_mip_bytes(uint32_t C, uint32_t H) { return kMipHeaderBytes + 2 * (size_t)C * (H >> kMipShift) * (H >> kMipShift) * (H >> kMipShift) / 8; }
 
 extern "C" int ntx_build_occupancy_mip(const uint8_t* grid, uint32_t C, uint32_t H, uint8_t* mip, ntx_stream_t stream) {
     NTX_REQUIRE(grid && mip, NTX_ERR_INVALID_ARGUMENT, "build_occupancy_mip: null pointer");
     NTX_REQUIRE(C >= 1 && C <= 16 && H >= 16 && H <= 1024 && (H & (H - 1)) == 0, NTX_ERR_UNSUPPORTED, "build_occupancy_mip: H must be a power of two in [16, 1024]");
     NTX_REQUIRE((reinterpret_cast<uintptr_t>(grid) & 15) == 0, NTX_ERR_INVALID_ARGUMENT, "build_occupancy_mip: bit-field must be 16-byte aligned");
-    const uint32_t Hc = H / 8, cells = C * Hc * Hc * Hc;
-    uint8_t* raw = mip + cells / 8;
-    occupancy_mip_raw_kernel<<<ceil_div<uint32_t>(cells / 8, 128), 128, 0, ST(stream)>>>(grid, cells, raw);
-    occupancy_mip_dilate_kernel<<<ceil_div<uint32_t>(cells / 8, 128), 128, 0, ST(stream)>>>(raw, C, Hc, mip);
+    const uint32_t Hc = H >> kMipShift, cells = C * Hc * Hc * Hc;
+    uint8_t* dil = mip + kMipHeaderBytes;
+    uint8_t* raw = dil + cells / 8;
+    occupancy_mip_init_kernel<<<1, 128, 0, ST(stream)>>>(reinterpret_cast<int*>(mip), C);
+    occupancy_mip_raw_kernel<<<ceil_div<uint32_t>(cells / 8, 128), 128, 0, ST(stream)>>>(grid, cells, Hc * Hc * Hc, raw, reinterpret_cast<int*>(mip));
+    occupancy_mip_dilate_kernel<<<ceil_div<uint32_t>(cells / 8, 128), 128, 0, ST(stream)>>>(raw, C, Hc, dil);
     return check_launch("build_occupancy_mip");
 }
 
