@@ -20,7 +20,7 @@ SOURCES = ["api.cu", "grid.cu", "sh.cu", "raymarch.cu", "mlp.cu", "mlp_bwd.cu", 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr", "-Xptxas", "-v",
-]
+] + os.environ.get("NTX_NVCC_EXTRA", "").split()   # development only, e.g. -DNTX_DEV_PROBES (tools/field_probe.py)
 
 
 def _nvcc():

@@ -16,7 +16,6 @@ const Tunables& tunables() {
     static Tunables t = [] {
         Tunables v;
         const char* e;
-        v.l1_keep_bytes = (e = getenv("NTX_L1_KEEP_BYTES")) ? (uint32_t)strtoul(e, nullptr, 0) : 0xffffffffu;
         v.field_ctas = (e = getenv("NTX_FIELD_CTAS")) ? atoi(e) : 0;
         v.pair_ctas = (e = getenv("NTX_PAIR_CTAS")) ? atoi(e) : 0;
         return v;

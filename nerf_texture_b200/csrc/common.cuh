@@ -24,7 +24,6 @@ void set_error(const char* fmt, ...);
 
 // run-time tuning knobs (environment variables, read once): experiments without rebuilding
 struct Tunables {
-    uint32_t l1_keep_bytes;  // NTX_L1_KEEP_BYTES: grid levels up to this size use L1-allocating loads, larger ones L1::no_allocate
     int field_ctas;          // NTX_FIELD_CTAS: resident CTAs per SM of the fused field kernel (0 = as many as fit)
     int pair_ctas;           // NTX_PAIR_CTAS: same for the stand-alone pair gather kernel
 };

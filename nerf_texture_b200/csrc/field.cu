@@ -49,7 +49,7 @@ __host__ __device__ inline FieldPlan field_plan(uint32_t L, uint32_t ns, uint32_
     p.ac_off = p.a0_off + kStages * p.a0_stage;
     p.h_off = p.ac_off + kStages * p.ac_stage;
     p.lv_off = p.h_off + kTileRows * kFW * 2u;
-    p.misc_off = p.lv_off + (uint32_t)sizeof(GridLevel) * kFieldMaxLevels;
+    p.misc_off = p.lv_off + (uint32_t)sizeof(PairLevel) * kFieldMaxLevels;
     p.total = p.misc_off + 128u;
     return p;
 }
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
     const float* __restrict__ xyz, const float* __restrict__ dirs, const float* __restrict__ deltas, const uint32_t M, const float bound,
     const __half* __restrict__ table, const int* __restrict__ offsets, const uint32_t L, const float S, const uint32_t H, const bool align,
     const __half* __restrict__ w_sigma, const __half* __restrict__ w_color, const uint32_t ns, const uint32_t nc, const float density_scale,
-    float* __restrict__ sigmas, float* __restrict__ rgbs, const uint32_t keep_bytes) {
+    float* __restrict__ sigmas, float* __restrict__ rgbs, const uint32_t dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const FieldPlan plan = field_plan(L, ns, nc);
     uint8_t* ws_smem = smem + plan.ws_off;
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
     uint8_t* a0_smem = smem + plan.a0_off;   // kStages tiles
     uint8_t* ac_smem = smem + plan.ac_off;   // kStages tiles
     uint8_t* h_smem = smem + plan.h_off;
-    GridLevel* lv = reinterpret_cast<GridLevel*>(smem + plan.lv_off);
+    PairLevel* lv = reinterpret_cast<PairLevel*>(smem + plan.lv_off);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + plan.misc_off);        // [kStages] producers -> consumer
     uint64_t* empty_bar = full_bar + kStages;                                      // [kStages] consumer (MMA completion) -> producers
     uint64_t* mma_bar = empty_bar + kStages;                                       // layer done -> consumer warps
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
         tc::fence_mbar_init();
     }
     if (warp == 0) tc::tmem_alloc<64>(tmem_slot);
-    if (tid < L) lv[tid] = make_level<3>(offsets, tid, S, H, /*gridtype=*/0, align);
+    if (tid < L) lv[tid] = make_pair_level(make_level<3>(offsets, tid, S, H, /*gridtype=*/0, align), table);
     {
         const __half* w = w_sigma; uint8_t* dst = ws_smem;
         load_matrix_kmajor(dst, w, kFW, K0, tid, kFieldThreads); w += (size_t)kFW * K0; dst += (size_t)kFW * K0 * 2;
@@ -154,7 +154,10 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
             uint8_t* ac = ac_smem + s * plan.ac_stage;
             for (uint32_t l0 = 0; l0 < L; l0 += 4) {
                 uint32_t packed[2];
-                pair_gather4<__half>(x, y, z, live, p, lv + l0, table, half_off, keep_bytes, packed);
+#ifdef NTX_DEV_PROBES
+                if (dbg & 1u) { packed[0] = packed[1] = 0; } else
+#endif
+                pair_gather4<__half>(x, y, z, live, p, lv + l0, half_off, packed);
                 // lane p owns levels l0+2p, l0+2p+1 -> 4 consecutive halfs (8 bytes) of the row
                 const uint32_t kcol = 2 * (l0 + 2 * p);
                 *reinterpret_cast<uint2*>(a0 + kmajor_off(srow, kcol, K0)) = make_uint2(packed[0], packed[1]);
@@ -162,11 +165,11 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
             // SH of the view direction (fp32, rounded to fp16 when it enters the fp16 MLP): lane p writes 8 of the 16 values
             float sh[16];
             sh_basis<4, false>(dx, dy, dz, sh, nullptr, nullptr, nullptr);
-            uint4 o;
-            o.x = float2_to_half2_bits(sh[8 * p + 0], sh[8 * p + 1]);
-            o.y = float2_to_half2_bits(sh[8 * p + 2], sh[8 * p + 3]);
-            o.z = float2_to_half2_bits(sh[8 * p + 4], sh[8 * p + 5]);
-            o.w = float2_to_half2_bits(sh[8 * p + 6], sh[8 * p + 7]);
+            uint4 o;   // (selects, not sh[8 * p + i]: a dynamic index would put the array in local memory)
+            o.x = p ? float2_to_half2_bits(sh[8], sh[9]) : float2_to_half2_bits(sh[0], sh[1]);
+            o.y = p ? float2_to_half2_bits(sh[10], sh[11]) : float2_to_half2_bits(sh[2], sh[3]);
+            o.z = p ? float2_to_half2_bits(sh[12], sh[13]) : float2_to_half2_bits(sh[4], sh[5]);
+            o.w = p ? float2_to_half2_bits(sh[14], sh[15]) : float2_to_half2_bits(sh[6], sh[7]);
             *reinterpret_cast<uint4*>(ac + kmajor_chunk_off(srow, p, kColorIn)) = o;
             tc::fence_proxy_async_smem();          // my generic-proxy writes -> visible to the tensor core's async proxy
             __syncwarp();
@@ -187,6 +190,13 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
 
             tc::mbar_wait(&full_bar[s], use & 1u);
             tc::tc_fence_after_sync();
+#ifdef NTX_DEV_PROBES
+            if (dbg & 2u) {   // producer-only timing: release the slot at once, skip both MLPs
+                if (tid == 0) tc::mbar_arrive(&empty_bar[s]);
+                if (b < M) { st_stream_f32(sigmas + b, 0.f); for (int c = 0; c < 3; c++) st_stream_f32(rgbs + (size_t)b * 3 + c, 0.f); }
+                continue;
+            }
+#endif
             // ---------------- sigma net ------------------------------------------------------------------------
             if (tid == 0) { issue_layer(a0_addr, ws_addr, K0, kFW, tmem_base); tc::mma_commit(mma_bar); }
             tc::mbar_wait(mma_bar, mma_phase); mma_phase ^= 1;
@@ -277,6 +287,17 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
 
 using namespace ntx;
 
+// development probes (only in builds with -DNTX_DEV_PROBES; tools/field_probe.py): bit 0 = producers skip the gather,
+// bit 1 = consumers skip the MLPs.  Product builds always pass 0 and the branches do not exist.
+static uint32_t dev_probe_flags() {
+#ifdef NTX_DEV_PROBES
+    const char* e = getenv("NTX_FIELD_DEBUG");
+    return e ? (uint32_t)atoi(e) : 0u;
+#else
+    return 0u;
+#endif
+}
+
 extern "C" int ntx_ngp_field_forward(const float* xyz, const float* dirs, const float* deltas, uint32_t M, float bound, const void* embeddings_f16,
                                      const int* offsets, uint32_t L, float S, uint32_t H, int align_corners, const void* w_sigma_f16,
                                      const void* w_color_f16, float density_scale, float* sigmas, float* rgbs, ntx_stream_t stream) {
@@ -307,7 +328,6 @@ extern "C" int ntx_ngp_field_forward(const float* xyz, const float* dirs, const 
     const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)(occ * sms));
     ngp_field_kernel<<<grid, kFieldThreads, plan.total, reinterpret_cast<cudaStream_t>(stream)>>>(
         xyz, dirs, deltas, M, bound, static_cast<const __half*>(embeddings_f16), offsets, L, S, H, align_corners != 0,
-        static_cast<const __half*>(w_sigma_f16), static_cast<const __half*>(w_color_f16), ns, nc, density_scale, sigmas, rgbs,
-        tunables().l1_keep_bytes);
+        static_cast<const __half*>(w_sigma_f16), static_cast<const __half*>(w_color_f16), ns, nc, density_scale, sigmas, rgbs, dev_probe_flags());
     return check_launch("ngp_field_forward");
 }

@@ -139,11 +139,11 @@ template <typename scalar_t>
 __global__ void __launch_bounds__(kPairThreads, 3) grid_fwd_pair_kernel(
     const float* __restrict__ inputs, const scalar_t* __restrict__ grid, const int* __restrict__ offsets,
     scalar_t* __restrict__ outputs, const uint32_t B, const uint32_t L, const float S, const uint32_t H,
-    const uint32_t gridtype, const bool align, const int layout, const uint32_t keep_bytes) {
+    const uint32_t gridtype, const bool align, const int layout) {
     using E = Elem2<scalar_t>;
     using raw = typename E::raw;
-    __shared__ GridLevel lv[kPairMaxLevels];
-    if (threadIdx.x < L) lv[threadIdx.x] = make_level<3>(offsets, threadIdx.x, S, H, gridtype, align);
+    __shared__ PairLevel lv[kPairMaxLevels];
+    if (threadIdx.x < L) lv[threadIdx.x] = make_pair_level(make_level<3>(offsets, threadIdx.x, S, H, gridtype, align), grid);
     __syncthreads();
 
     const uint32_t p = threadIdx.x & 1u;  // which x corner this lane gathers
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kPairThreads, 3) grid_fwd_pair_kernel(
 
         for (uint32_t l0 = 0; l0 < L; l0 += 4) {
             raw packed[2];
-            pair_gather4<scalar_t>(x, y, z, live, p, lv + l0, grid, half_off, keep_bytes, packed);
+            pair_gather4<scalar_t>(x, y, z, live, p, lv + l0, half_off, packed);
             if (valid) {
                 const uint32_t la = l0 + 2 * p;
                 if (layout == NTX_LAYOUT_BLC) {
@@ -319,8 +319,7 @@ static int launch_fwd_pair(const float* inputs, const scalar_t* emb, const int* 
         if (tunables().pair_ctas > 0) grid_cap = tunables().pair_ctas * device_sm_count();
     }
     const uint32_t groups = ceil_div<uint32_t>(B, kPairThreads / 2);
-    grid_fwd_pair_kernel<scalar_t><<<min(groups, (uint32_t)grid_cap), kPairThreads, 0, st>>>(inputs, emb, offsets, out, B, L, S, H, gridtype, align, layout,
-                                                                                             tunables().l1_keep_bytes);
+    grid_fwd_pair_kernel<scalar_t><<<min(groups, (uint32_t)grid_cap), kPairThreads, 0, st>>>(inputs, emb, offsets, out, B, L, S, H, gridtype, align, layout);
     return check_launch("grid_encode_forward(pair)");
 }
 

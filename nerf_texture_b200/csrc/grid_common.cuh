@@ -65,18 +65,33 @@ __device__ __forceinline__ uint32_t corner_index(const GridLevel& g, const uint3
 static __device__ __noinline__ uint32_t slow_umod(uint32_t a, uint32_t b) { return a % b; }
 
 // ---------------------------------------------------------------------------------------------------- lane-pair gather
+// per-level record of the pair gather: 32 bytes = two LDS.128, with the level's table pointer resolved once per CTA so that
+// a corner address is a single IMAD.WIDE (index * elem + base)
+struct PairLevel {
+    float scale;
+    uint32_t hs, sy, sz;
+    const void* base;      // grid + offset * 2
+    uint32_t mask;
+    uint32_t kind;         // 0 generic | 1 hashed, power-of-two table, scale < 2^22 (the hot path of the fine levels)
+    __device__ __forceinline__ uint32_t use_hash() const { return kind >> 1; }
+};
+template <typename scalar_t>
+__device__ __forceinline__ PairLevel make_pair_level(const GridLevel& g, const scalar_t* __restrict__ grid) {
+    PairLevel q;
+    q.scale = g.scale; q.hs = g.hs; q.sy = g.sy; q.sz = g.sz; q.mask = g.mask;
+    q.base = grid + (size_t)g.offset * 2;
+    q.kind = (g.use_hash && g.mask && g.scale < 4194304.0f) ? 1u : 0u;
+    q.kind |= g.use_hash << 1;
+    return q;
+}
+
 // D = 3, C = 2.  Raw table element = 2 scalars: u32 for half2, u64 for float2.
 template <typename scalar_t> struct Elem2;
 template <> struct Elem2<__half> {
     using raw = uint32_t;
     using accum = __half2;
-    // hashed levels are far larger than L1 and touched at random: do not let them evict the small dense levels
-    static __device__ __forceinline__ raw load(const void* p, bool keep_l1) {
-        raw r;
-        if (keep_l1) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
-        else asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
-        return r;
-    }
+    // plain read-only loads: L1::no_allocate on the big hashed levels was measured 2-4x SLOWER (profiles/r01_summary.md)
+    static __device__ __forceinline__ raw load(const void* p) { return __ldg(reinterpret_cast<const raw*>(p)); }
     static __device__ __forceinline__ raw xchg(raw v) { return __shfl_xor_sync(0xffffffffu, v, 1); }
     static __device__ __forceinline__ accum zero() { return __floats2half2_rn(0.f, 0.f); }
     static __device__ __forceinline__ void add(accum& r, float w, raw v) {
@@ -91,12 +106,7 @@ template <> struct Elem2<__half> {
 template <> struct Elem2<float> {
     using raw = uint64_t;
     struct accum { float a, b; };
-    static __device__ __forceinline__ raw load(const void* p, bool keep_l1) {
-        raw r;
-        if (keep_l1) asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(r) : "l"(p));
-        else asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(p));
-        return r;
-    }
+    static __device__ __forceinline__ raw load(const void* p) { return __ldg(reinterpret_cast<const unsigned long long*>(p)); }
     static __device__ __forceinline__ raw xchg(raw v) { return __shfl_xor_sync(0xffffffffu, v, 1); }
     static __device__ __forceinline__ accum zero() { return {0.f, 0.f}; }
     static __device__ __forceinline__ void add(accum& r, float w, raw v) {
@@ -113,8 +123,8 @@ template <> struct Elem2<float> {
 // Must be called by all 32 lanes of the warp (uses shuffles).  `live` = sample valid and inside [0,1]^3; coordinates of
 // non-live samples must have been forced to 0 by the caller (their loads then hit entry 0 of each level and are discarded).
 template <typename scalar_t>
-__device__ __forceinline__ void pair_gather4(const float x, const float y, const float z, const bool live, const uint32_t p, const GridLevel* __restrict__ lv,
-                                             const scalar_t* __restrict__ grid, const float half_off, const uint32_t keep_bytes,
+__device__ __forceinline__ void pair_gather4(const float x, const float y, const float z, const bool live, const uint32_t p, const PairLevel* __restrict__ lv,
+                                             const float half_off,
                                              typename Elem2<scalar_t>::raw packed[2]) {
     using E = Elem2<scalar_t>;
     using raw = typename E::raw;
@@ -122,31 +132,37 @@ __device__ __forceinline__ void pair_gather4(const float x, const float y, const
     float fx[4], fy[4], fz[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const GridLevel g = lv[j];
+        const PairLevel g = lv[j];
         const float px = __fmaf_rn(x, g.scale, half_off), py = __fmaf_rn(y, g.scale, half_off), pz = __fmaf_rn(z, g.scale, half_off);
-        const float flx = floorf(px), fly = floorf(py), flz = floorf(pz);
-        fx[j] = px - flx; fy[j] = py - fly; fz[j] = pz - flz;
-        const uint32_t cx = (uint32_t)flx + p, iy = (uint32_t)fly, iz = (uint32_t)flz;
-        const scalar_t* gl = grid + (size_t)g.offset * 2;
-        const bool keep = g.hs * (uint32_t)(2 * sizeof(scalar_t)) <= keep_bytes;  // whole level small enough to live in L1
-        if (g.use_hash && g.mask) {           // hashed level, power-of-two table: the hot path for fine levels
-            const uint32_t ty0 = iy * 2654435761u, ty1 = ty0 + 2654435761u, tz0 = iz * 805459861u, tz1 = tz0 + 805459861u;
+        const raw* gl = static_cast<const raw*>(g.base);
+        if (g.kind & 1u) {           // hashed level, power-of-two table: the hot path for fine levels
+            // floor of a non-negative float < 2^22 without the quarter-rate FRND/F2I: px + 2^23 rounded down has floor(px)
+            // in its mantissa, and subtracting 2^23 again is exact  (same values as floorf / (uint32_t) below)
+            const float bx = __fadd_rd(px, 8388608.0f), by = __fadd_rd(py, 8388608.0f), bz = __fadd_rd(pz, 8388608.0f);
+            fx[j] = px - (bx - 8388608.0f); fy[j] = py - (by - 8388608.0f); fz[j] = pz - (bz - 8388608.0f);
+            const uint32_t cx = (__float_as_uint(bx) - 0x4b000000u) + p;
+            const uint32_t ty0 = (__float_as_uint(by) - 0x4b000000u) * 2654435761u, ty1 = ty0 + 2654435761u;
+            const uint32_t tz0 = (__float_as_uint(bz) - 0x4b000000u) * 805459861u, tz1 = tz0 + 805459861u;
+            const uint32_t a0 = cx ^ ty0, a1 = cx ^ ty1;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                const uint32_t index = (cx ^ ((c & 1) ? ty1 : ty0) ^ ((c & 2) ? tz1 : tz0)) & g.mask;
-                v[j][c] = E::load(gl + (size_t)index * 2, keep);
+                const uint32_t index = (((c & 1) ? a1 : a0) ^ ((c & 2) ? tz1 : tz0)) & g.mask;
+                v[j][c] = E::load(gl + index);
             }
         } else {
+            const float flx = floorf(px), fly = floorf(py), flz = floorf(pz);
+            fx[j] = px - flx; fy[j] = py - fly; fz[j] = pz - flz;
+            const uint32_t cx = (uint32_t)flx + p, iy = (uint32_t)fly, iz = (uint32_t)flz;
             uint32_t ty0, ty1, tz0, tz1;
-            if (g.use_hash) { ty0 = iy * 2654435761u; ty1 = ty0 + 2654435761u; tz0 = iz * 805459861u; tz1 = tz0 + 805459861u; }
+            if (g.use_hash()) { ty0 = iy * 2654435761u; ty1 = ty0 + 2654435761u; tz0 = iz * 805459861u; tz1 = tz0 + 805459861u; }
             else { ty0 = iy * g.sy; ty1 = ty0 + g.sy; tz0 = iz * g.sz; tz1 = tz0 + g.sz; }
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 const uint32_t ty = (c & 1) ? ty1 : ty0, tz = (c & 2) ? tz1 : tz0;
-                uint32_t index = g.use_hash ? (cx ^ ty ^ tz) : (cx + ty + tz);
+                uint32_t index = g.use_hash() ? (cx ^ ty ^ tz) : (cx + ty + tz);
                 // dense levels only leave [0, hs) when a coordinate is exactly 1.0 (corner res) — rare, keep it a branch
                 if (__builtin_expect(index >= g.hs, 0)) index = g.mask ? (index & g.mask) : slow_umod(index, g.hs);
-                v[j][c] = E::load(gl + (size_t)index * 2, keep);
+                v[j][c] = E::load(gl + index);
             }
         }
     }

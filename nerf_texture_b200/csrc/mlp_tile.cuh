@@ -75,7 +75,9 @@ __device__ __forceinline__ uint32_t act_pack2(uint32_t act, uint32_t a_bits, uin
     const __half2 h = __floats2half2_rn(__uint_as_float(a_bits), __uint_as_float(b_bits));
     if (act == 0) {
         const __half2 z = __floats2half2_rn(0.f, 0.f);
-        const __half2 r = __hmul2(h, __hgt2(h, z));  // x * (x > 0)
+        // the reference writes ReLU as x * (x > 0) (NaN-propagating; negative x gives -0).  max(x, 0) with NaN propagation is
+        // one instruction instead of two and differs only in the sign of that zero, which nothing downstream can observe
+        const __half2 r = __hmax2_nan(h, z);
         return *reinterpret_cast<const uint32_t*>(&r);
     }
     if (act >= 6) return *reinterpret_cast<const uint32_t*>(&h);
