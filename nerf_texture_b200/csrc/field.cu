@@ -8,13 +8,16 @@
 // The reference runs this as 4 extension calls + ~10 torch glue kernels with every intermediate (features 64 B, padded
 // copies, geo_feat, SH 64 B, concatenated colour input 64 B ...) making a round trip through HBM.
 // Here a CTA owns 128-sample tiles and is warp-specialised:
-//   * 8 producer warps (256 threads = 128 lane pairs) gather the features of a tile straight into the shared-memory A
-//     operand of the first UMMA and evaluate SH into the colour net's A operand, then move on to the next tile;
+//   * 12 producer warps gather features straight into the shared-memory A operand of the first UMMA and evaluate SH into
+//     the colour net's A operand.  A warp (16 lane pairs) takes 16-row slices of the CTA's tile sequence round-robin, so
+//     the producers run up to two tiles ahead of the consumers;
 //   * 4 consumer warps (one per TMEM lane quarter) run the two MLPs of the previous tile: one thread issues the
 //     tcgen05.mma of a layer, the warps pull the accumulator out of TMEM, apply ReLU, round to fp16 and write the next
 //     layer's A operand; geo_feat goes from the sigma net's accumulator into the colour net's A tile;
-//   * a 2-slot ring of A tiles with full/empty mbarriers decouples them, so the latency-bound MMA->epilogue chain (7
-//     dependent stages per tile) hides behind the L1-bound gather instead of serialising with it.
+//   * a 3-slot ring of A tiles with full/empty mbarriers decouples them, so the latency-bound MMA->epilogue chain (7
+//     dependent stages per tile) hides behind the gather instead of serialising with it;
+//   * the gather is bound by loads in flight and issue slots, i.e. by resident producer warps (tools/field_probe.py): the
+//     kernel is held to 64 registers so that 2 CTAs x (12 producer + 4 consumer) warps fit on an SM.
 // Only xyz/dir (24 B) come in and sigma/rgb (16 B) go out per sample.
 #include "grid_common.cuh"
 #include "mlp_tile.cuh"
@@ -23,18 +26,21 @@
 namespace ntx {
 
 constexpr int kConsumerWarps = 4;
-constexpr int kProducerWarps = 8;
-constexpr int kFieldThreads = 32 * (kConsumerWarps + kProducerWarps);   // 384
+constexpr int kProducerWarps = 12;
+constexpr int kTaskRows = 16;                                            // rows one producer warp gathers at a time
+constexpr int kTasksPerTile = 8;                                         // kTileRows / kTaskRows
+constexpr int kFieldThreads = 32 * (kConsumerWarps + kProducerWarps);   // 512
 constexpr int kFW = 64;          // hidden width of both MLPs
 constexpr int kColorIn = 32;     // SH(16) + geo_feat(15) + zero pad (network_ff.py:42,95-97)
+constexpr int kShDim = 16;       // SH degree 4
 constexpr int kFieldMaxLevels = 32;
-constexpr int kStages = 2;
+constexpr int kStages = 3;
 
 struct FieldPlan {
     uint32_t k0;                 // sigma-net input width = 2L
     uint32_t ws_bytes, wc_bytes; // weight bytes of the two nets
-    uint32_t ws_off, wc_off, a0_off, ac_off, h_off, lv_off, misc_off, total;
-    uint32_t a0_stage, ac_stage;
+    uint32_t ws_off, wc_off, a0_off, h_off, lv_off, misc_off, total;
+    uint32_t a0_stage;
 };
 __host__ __device__ inline FieldPlan field_plan(uint32_t L, uint32_t ns, uint32_t nc) {
     FieldPlan p;
@@ -44,10 +50,8 @@ __host__ __device__ inline FieldPlan field_plan(uint32_t L, uint32_t ns, uint32_
     p.ws_off = 0;
     p.wc_off = p.ws_off + p.ws_bytes;
     p.a0_stage = kTileRows * p.k0 * 2u;
-    p.ac_stage = kTileRows * kColorIn * 2u;
     p.a0_off = (p.wc_off + p.wc_bytes + 127u) & ~127u;
-    p.ac_off = p.a0_off + kStages * p.a0_stage;
-    p.h_off = p.ac_off + kStages * p.ac_stage;
+    p.h_off = p.a0_off + kStages * p.a0_stage;
     p.lv_off = p.h_off + kTileRows * kFW * 2u;
     p.misc_off = p.lv_off + (uint32_t)sizeof(PairLevel) * kFieldMaxLevels;
     p.total = p.misc_off + 128u;
@@ -56,17 +60,18 @@ __host__ __device__ inline FieldPlan field_plan(uint32_t L, uint32_t ns, uint32_
 
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kConsumerWarps) : "memory"); }
 
-// hidden-layer epilogue (4 consumer warps, warp w owns TMEM lanes 32w..32w+31 = tile rows): two 32-column passes
+// hidden-layer epilogue (4 consumer warps, warp w owns TMEM lanes 32w..32w+31 = tile rows): four 16-column passes
+// (keeps the consumer inside the kernel's 64-register budget)
 __device__ __forceinline__ void field_hidden_epilogue(uint32_t tmem_base, uint8_t* h_smem, uint32_t warp, uint32_t lane) {
     const uint32_t row = warp * 32 + lane;
 #pragma unroll
-    for (int half_sel = 0; half_sel < 2; half_sel++) {
-        const uint32_t col = half_sel * 32;
-        uint32_t v[32];
-        tc::tmem_ld_x32(tmem_base + ((warp * 32u) << 16) + col, v);
+    for (int q = 0; q < 4; q++) {
+        const uint32_t col = q * 16;
+        uint32_t v[16];
+        tc::tmem_ld_x16(tmem_base + ((warp * 32u) << 16) + col, v);
         tc::tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
+        for (int j = 0; j < 16; j += 8) {
             uint4 o;
             o.x = act_pack2(0, v[j + 0], v[j + 1]);
             o.y = act_pack2(0, v[j + 2], v[j + 3]);
@@ -87,7 +92,6 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
     uint8_t* ws_smem = smem + plan.ws_off;
     uint8_t* wc_smem = smem + plan.wc_off;
     uint8_t* a0_smem = smem + plan.a0_off;   // kStages tiles
-    uint8_t* ac_smem = smem + plan.ac_off;   // kStages tiles
     uint8_t* h_smem = smem + plan.h_off;
     PairLevel* lv = reinterpret_cast<PairLevel*>(smem + plan.lv_off);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + plan.misc_off);        // [kStages] producers -> consumer
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
 
     // ---- one-time setup (all 12 warps) ---------------------------------------------------------------------------
     if (tid == 0) {
-        for (int s = 0; s < kStages; s++) { tc::mbar_init(&full_bar[s], kProducerWarps); tc::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kStages; s++) { tc::mbar_init(&full_bar[s], kTasksPerTile); tc::mbar_init(&empty_bar[s], 1); }
         tc::mbar_init(mma_bar, 1);
         tc::fence_mbar_init();
     }
@@ -125,33 +129,33 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
 
     if (warp >= kConsumerWarps) {
         // =============================== PRODUCERS: gather + SH =====================================================
-        const uint32_t ptid = tid - 32 * kConsumerWarps;      // 0..255
-        const uint32_t p = ptid & 1u;                          // which x corner this lane gathers
-        const uint32_t srow = ptid >> 1;                       // sample row of this lane pair inside the tile
+        const uint32_t pw = warp - kConsumerWarps;             // 0..11
+        const uint32_t p = lane & 1u;                          // which x corner this lane gathers
         const float half_off = align ? 0.0f : 0.5f;
         // GridEncoder.forward: inputs = (inputs + bound) / (2 * bound) (grid.py:143).  torch's CUDA true-division by a Python
         // scalar multiplies by the fp32 reciprocal (BinaryDivTrueKernel.cu), so do exactly that.
         const float inv2b = 1.0f / (2.0f * bound);
-        uint32_t k = 0;
-        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+        for (uint32_t task = pw;; task += kProducerWarps) {
+            const uint32_t k = task / kTasksPerTile;            // k-th tile of this CTA
+            const uint32_t tile = blockIdx.x + k * gridDim.x;
+            if (tile >= ntiles) break;
             const uint32_t s = k % kStages, use = k / kStages;
+            const uint32_t srow = (task % kTasksPerTile) * kTaskRows + (lane >> 1);   // row of this lane pair inside the tile
             const uint32_t b = tile * kTileRows + srow;
             const bool valid = b < M;
-            float x = 0.f, y = 0.f, z = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+            float x = 0.f, y = 0.f, z = 0.f;
             bool skip = !valid;
             if (valid) {
                 x = __fmul_rn(__fadd_rn(xyz[(size_t)b * 3], bound), inv2b);
                 y = __fmul_rn(__fadd_rn(xyz[(size_t)b * 3 + 1], bound), inv2b);
                 z = __fmul_rn(__fadd_rn(xyz[(size_t)b * 3 + 2], bound), inv2b);
-                dx = dirs[(size_t)b * 3]; dy = dirs[(size_t)b * 3 + 1]; dz = dirs[(size_t)b * 3 + 2];
                 if (deltas && deltas[(size_t)b * 2] == 0.0f) skip = true;  // sentinel slot of march_rays
             }
             const bool oob = (x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1);
             const bool live = !skip && !oob;
             if (!live) { x = 0.f; y = 0.f; z = 0.f; }  // keeps the (discarded) loads of dead lanes in bounds
-            tc::mbar_wait(&empty_bar[s], (use & 1u) ^ 1u);   // slot free? (first use of a slot passes immediately)
+            tc::mbar_wait_relaxed(&empty_bar[s], (use & 1u) ^ 1u);   // slot free? (first use of a slot passes immediately)
             uint8_t* a0 = a0_smem + s * plan.a0_stage;
-            uint8_t* ac = ac_smem + s * plan.ac_stage;
             for (uint32_t l0 = 0; l0 < L; l0 += 4) {
                 uint32_t packed[2];
 #ifdef NTX_DEV_PROBES
@@ -162,15 +166,6 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
                 const uint32_t kcol = 2 * (l0 + 2 * p);
                 *reinterpret_cast<uint2*>(a0 + kmajor_off(srow, kcol, K0)) = make_uint2(packed[0], packed[1]);
             }
-            // SH of the view direction (fp32, rounded to fp16 when it enters the fp16 MLP): lane p writes 8 of the 16 values
-            float sh[16];
-            sh_basis<4, false>(dx, dy, dz, sh, nullptr, nullptr, nullptr);
-            uint4 o;   // (selects, not sh[8 * p + i]: a dynamic index would put the array in local memory)
-            o.x = p ? float2_to_half2_bits(sh[8], sh[9]) : float2_to_half2_bits(sh[0], sh[1]);
-            o.y = p ? float2_to_half2_bits(sh[10], sh[11]) : float2_to_half2_bits(sh[2], sh[3]);
-            o.z = p ? float2_to_half2_bits(sh[12], sh[13]) : float2_to_half2_bits(sh[4], sh[5]);
-            o.w = p ? float2_to_half2_bits(sh[14], sh[15]) : float2_to_half2_bits(sh[6], sh[7]);
-            *reinterpret_cast<uint4*>(ac + kmajor_chunk_off(srow, p, kColorIn)) = o;
             tc::fence_proxy_async_smem();          // my generic-proxy writes -> visible to the tensor core's async proxy
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&full_bar[s]);
@@ -182,11 +177,12 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
         uint32_t k = 0;
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
             const uint32_t s = k % kStages, use = k / kStages;
-            const uint32_t a0_addr = tc::smem_u32(a0_smem + s * plan.a0_stage), ac_addr = tc::smem_u32(ac_smem + s * plan.ac_stage);
-            uint8_t* ac = ac_smem + s * plan.ac_stage;
+            const uint32_t a0_addr = tc::smem_u32(a0_smem + s * plan.a0_stage);
             const uint32_t row = warp * 32 + lane;
             const uint32_t b = tile * kTileRows + row;
             const bool dead = (b >= M) || (deltas && deltas[(size_t)b * 2] == 0.0f);
+            float dx = 0.f, dy = 0.f, dz = 0.f;     // view direction of this row: its SH basis is evaluated between the two nets
+            if (b < M) { dx = dirs[(size_t)b * 3]; dy = dirs[(size_t)b * 3 + 1]; dz = dirs[(size_t)b * 3 + 2]; }
 
             tc::mbar_wait(&full_bar[s], use & 1u);
             tc::tc_fence_after_sync();
@@ -198,7 +194,11 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
             }
 #endif
             // ---------------- sigma net ------------------------------------------------------------------------
-            if (tid == 0) { issue_layer(a0_addr, ws_addr, K0, kFW, tmem_base); tc::mma_commit(mma_bar); }
+            if (tid == 0) {
+                issue_layer(a0_addr, ws_addr, K0, kFW, tmem_base);
+                tc::mma_commit(mma_bar);
+                tc::mma_commit(&empty_bar[s]);   // the feature tile is free again as soon as this MMA has read it
+            }
             tc::mbar_wait(mma_bar, mma_phase); mma_phase ^= 1;
             tc::tc_fence_after_sync();
             field_hidden_epilogue(tmem_base, h_smem, warp, lane);
@@ -225,23 +225,34 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
                 for (int j = 0; j < 8; j++) hb[j] = float2_to_half2_bits(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
                 const float h0 = __low2float(*reinterpret_cast<const __half2*>(&hb[0]));
                 if (b < M) st_stream_f32(sigmas + b, dead ? 0.0f : density_scale * expf(h0));
-                // colour-net input columns 16..31 = h[1..15], 0   (network_ff.py:95-97)
+                // colour-net input [128 x 32] = SH(dir) ++ h[1..15] ++ 0   (network_ff.py:93-97), built at the start of h_smem: the
+                // hidden activations there are dead (the output-layer MMA has completed), and the colour net's first epilogue
+                // overwrites it only after its MMA has read it.
                 uint4 c2, c3;
                 c2.x = __byte_perm(hb[0], hb[1], 0x5432); c2.y = __byte_perm(hb[1], hb[2], 0x5432);
                 c2.z = __byte_perm(hb[2], hb[3], 0x5432); c2.w = __byte_perm(hb[3], hb[4], 0x5432);
                 c3.x = __byte_perm(hb[4], hb[5], 0x5432); c3.y = __byte_perm(hb[5], hb[6], 0x5432);
                 c3.z = __byte_perm(hb[6], hb[7], 0x5432); c3.w = __byte_perm(hb[7], 0u, 0x5432);
-                *reinterpret_cast<uint4*>(ac + kmajor_chunk_off(row, 2, kColorIn)) = c2;
-                *reinterpret_cast<uint4*>(ac + kmajor_chunk_off(row, 3, kColorIn)) = c3;
+                *reinterpret_cast<uint4*>(h_smem + kmajor_chunk_off(row, 2, kColorIn)) = c2;
+                *reinterpret_cast<uint4*>(h_smem + kmajor_chunk_off(row, 3, kColorIn)) = c3;
+                // SH of the view direction (fp32, rounded to fp16 when it enters the fp16 MLP)
+                float sh[16];
+                sh_basis<4, false>(dx, dy, dz, sh, nullptr, nullptr, nullptr);
+                uint4 s0, s1;
+                s0.x = float2_to_half2_bits(sh[0], sh[1]); s0.y = float2_to_half2_bits(sh[2], sh[3]);
+                s0.z = float2_to_half2_bits(sh[4], sh[5]); s0.w = float2_to_half2_bits(sh[6], sh[7]);
+                s1.x = float2_to_half2_bits(sh[8], sh[9]); s1.y = float2_to_half2_bits(sh[10], sh[11]);
+                s1.z = float2_to_half2_bits(sh[12], sh[13]); s1.w = float2_to_half2_bits(sh[14], sh[15]);
+                *reinterpret_cast<uint4*>(h_smem + kmajor_chunk_off(row, 0, kColorIn)) = s0;
+                *reinterpret_cast<uint4*>(h_smem + kmajor_chunk_off(row, 1, kColorIn)) = s1;
             }
             tc::fence_proxy_async_smem(); tc::tc_fence_before_sync(); consumer_sync();
 
             // ---------------- colour net -----------------------------------------------------------------------
             if (tid == 0) {
                 tc::tc_fence_after_sync();
-                issue_layer(ac_addr, wc_addr, kColorIn, kFW, tmem_base);
+                issue_layer(h_addr, wc_addr, kColorIn, kFW, tmem_base);
                 tc::mma_commit(mma_bar);
-                tc::mma_commit(&empty_bar[s]);   // both A tiles of this slot have been consumed once these MMAs retire
             }
             tc::mbar_wait(mma_bar, mma_phase); mma_phase ^= 1;
             tc::tc_fence_after_sync();

@@ -317,6 +317,8 @@ static int launch_fwd_pair(const float* inputs, const scalar_t* emb, const int* 
     if (!grid_cap) {
         grid_cap = persistent_grid((const void*)grid_fwd_pair_kernel<scalar_t>, kPairThreads, 0);
         if (tunables().pair_ctas > 0) grid_cap = tunables().pair_ctas * device_sm_count();
+        if (const char* e = getenv("NTX_PAIR_CARVEOUT"))   // experiment: shrink L1 by forcing a shared-memory carve-out (percent)
+            cudaFuncSetAttribute((const void*)grid_fwd_pair_kernel<scalar_t>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
     }
     const uint32_t groups = ceil_div<uint32_t>(B, kPairThreads / 2);
     grid_fwd_pair_kernel<scalar_t><<<min(groups, (uint32_t)grid_cap), kPairThreads, 0, st>>>(inputs, emb, offsets, out, B, L, S, H, gridtype, align, layout);

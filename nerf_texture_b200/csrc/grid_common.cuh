@@ -72,8 +72,10 @@ struct PairLevel {
     uint32_t hs, sy, sz;
     const void* base;      // grid + offset * 2
     uint32_t mask;
-    uint32_t kind;         // 0 generic | 1 hashed, power-of-two table, scale < 2^22 (the hot path of the fine levels)
-    __device__ __forceinline__ uint32_t use_hash() const { return kind >> 1; }
+    uint32_t kind;         // bit 0: hashed, power-of-two table, scale < 2^22 (the hot path of the fine levels)
+                           // bit 1: dense (all three strides taken: plain x + y*R + z*R^2 addressing, a wrap needs a coordinate == R)
+                           // bit 2: use_hash (for the generic path, taken when neither fast bit is set)
+    __device__ __forceinline__ uint32_t use_hash() const { return kind >> 2; }
 };
 template <typename scalar_t>
 __device__ __forceinline__ PairLevel make_pair_level(const GridLevel& g, const scalar_t* __restrict__ grid) {
@@ -81,7 +83,9 @@ __device__ __forceinline__ PairLevel make_pair_level(const GridLevel& g, const s
     q.scale = g.scale; q.hs = g.hs; q.sy = g.sy; q.sz = g.sz; q.mask = g.mask;
     q.base = grid + (size_t)g.offset * 2;
     q.kind = (g.use_hash && g.mask && g.scale < 4194304.0f) ? 1u : 0u;
-    q.kind |= g.use_hash << 1;
+    // sy = R, sz = R^2; the level is a plain dense R^3 block iff the third stride was taken and R^3 fits the level
+    if (!g.use_hash && g.sz != 0 && (uint64_t)g.sz * g.sy <= g.hs && g.scale < 4194304.0f) q.kind |= 2u;
+    q.kind |= g.use_hash << 2;
     return q;
 }
 
@@ -149,6 +153,23 @@ __device__ __forceinline__ void pair_gather4(const float x, const float y, const
                 const uint32_t index = (((c & 1) ? a1 : a0) ^ ((c & 2) ? tz1 : tz0)) & g.mask;
                 v[j][c] = E::load(gl + index);
             }
+        } else if (g.kind & 2u) {    // dense coarse level: plain 3-D addressing
+            const float bx = __fadd_rd(px, 8388608.0f), by = __fadd_rd(py, 8388608.0f), bz = __fadd_rd(pz, 8388608.0f);
+            fx[j] = px - (bx - 8388608.0f); fy[j] = py - (by - 8388608.0f); fz[j] = pz - (bz - 8388608.0f);
+            uint32_t i00 = (__float_as_uint(bx) - 0x4b000000u) + p + (__float_as_uint(by) - 0x4b000000u) * g.sy + (__float_as_uint(bz) - 0x4b000000u) * g.sz;
+            uint32_t i01 = i00 + g.sy, i10 = i00 + g.sz, i11 = i01 + g.sz;
+            // with align_corners a coordinate of exactly 1.0 makes the far corner index R: the reference then wraps modulo
+            // the level size (gridencoder.cu:71).  i11 is the largest of the four, so one test covers them all.
+            if (__builtin_expect(i11 >= g.hs, 0)) {
+                i00 = i00 >= g.hs ? (g.mask ? (i00 & g.mask) : slow_umod(i00, g.hs)) : i00;
+                i01 = i01 >= g.hs ? (g.mask ? (i01 & g.mask) : slow_umod(i01, g.hs)) : i01;
+                i10 = i10 >= g.hs ? (g.mask ? (i10 & g.mask) : slow_umod(i10, g.hs)) : i10;
+                i11 = g.mask ? (i11 & g.mask) : slow_umod(i11, g.hs);
+            }
+            v[j][0] = E::load(gl + i00);
+            v[j][1] = E::load(gl + i01);
+            v[j][2] = E::load(gl + i10);
+            v[j][3] = E::load(gl + i11);
         } else {
             const float flx = floorf(px), fly = floorf(py), flz = floorf(pz);
             fx[j] = px - flx; fy[j] = py - fly; fz[j] = pz - flz;

@@ -32,6 +32,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// same for waits that are not latency-critical (a producer waiting for a free slot): the thread is suspended for up to
+// ~1 us per poll instead of burning issue slots the working warps of the SM need
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n .reg .pred p;\n"
+            " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            " selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done) : "r"(addr), "r"(parity), "r"(1000u) : "memory");
+        if (spin > (1u << 22)) __trap();
+    }
+}
+
 // ---- proxies / fences -----------------------------------------------------------------------------------
 // make this thread's generic-proxy shared-memory writes visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
