@@ -8,16 +8,19 @@
 // The reference runs this as 4 extension calls + ~10 torch glue kernels with every intermediate (features 64 B, padded
 // copies, geo_feat, SH 64 B, concatenated colour input 64 B ...) making a round trip through HBM.
 // Here a CTA owns 128-sample tiles and is warp-specialised:
-//   * 12 producer warps gather features straight into the shared-memory A operand of the first UMMA and evaluate SH into
-//     the colour net's A operand.  A warp (16 lane pairs) takes 16-row slices of the CTA's tile sequence round-robin, so
-//     the producers run up to two tiles ahead of the consumers;
-//   * 4 consumer warps (one per TMEM lane quarter) run the two MLPs of the previous tile: one thread issues the
-//     tcgen05.mma of a layer, the warps pull the accumulator out of TMEM, apply ReLU, round to fp16 and write the next
-//     layer's A operand; geo_feat goes from the sigma net's accumulator into the colour net's A tile;
-//   * a 3-slot ring of A tiles with full/empty mbarriers decouples them, so the latency-bound MMA->epilogue chain (7
-//     dependent stages per tile) hides behind the gather instead of serialising with it;
-//   * the gather is bound by loads in flight and issue slots, i.e. by resident producer warps (tools/field_probe.py): the
-//     kernel is held to 64 registers so that 2 CTAs x (12 producer + 4 consumer) warps fit on an SM.
+//   * 12 producer warps gather features straight into the shared-memory A operand of the first UMMA.  A warp (16 lane
+//     pairs) takes 16-row slices of the CTA's tile sequence round-robin, so the producers run up to kStages tiles ahead;
+//     the feature tile is handed back as soon as the first MMA has read it;
+//   * 4 consumer warps (one per TMEM lane quarter) run the two MLPs: one thread issues the tcgen05.mma of a layer, the
+//     warps pull the accumulator out of TMEM, apply ReLU, round to fp16 and write the next layer's A operand; between the
+//     nets they evaluate SH(dir) and put it next to geo_feat as the colour net's input;
+//   * the MMA -> epilogue chain is 7 dependent stages per tile and each stage is mostly latency (the issuing thread and
+//     the epilogue warps share their schedulers with the producers: measured ~900 cycles per stage of which the MMA is
+//     ~130, tools/field_probe.py).  The consumers therefore keep TWO tiles in flight (two TMEM accumulators, two
+//     activation buffers) and alternate between them stage by stage: while one tile's MMA runs, the other tile's epilogue
+//     does;
+//   * shared memory is kept under 100 KB per CTA on purpose: the gather's throughput follows the L1 capacity left over
+//     by the carve-out (228 KB carve-out: 2x slower, profiles/r01_summary.md).
 // Only xyz/dir (24 B) come in and sigma/rgb (16 B) go out per sample.
 #include "grid_common.cuh"
 #include "mlp_tile.cuh"
@@ -25,22 +28,23 @@
 
 namespace ntx {
 
-constexpr int kConsumerWarps = 4;
+constexpr int kConsumerWarps = 4;   // 4: one per TMEM lane quarter | 8: two per quarter, warp w reads lanes 32*(w&3).., columns 32*(w>>2)..
 constexpr int kProducerWarps = 12;
 constexpr int kTaskRows = 16;                                            // rows one producer warp gathers at a time
 constexpr int kTasksPerTile = 8;                                         // kTileRows / kTaskRows
 constexpr int kFieldThreads = 32 * (kConsumerWarps + kProducerWarps);   // 512
 constexpr int kFW = 64;          // hidden width of both MLPs
 constexpr int kColorIn = 32;     // SH(16) + geo_feat(15) + zero pad (network_ff.py:42,95-97)
-constexpr int kShDim = 16;       // SH degree 4
 constexpr int kFieldMaxLevels = 32;
-constexpr int kStages = 3;
+constexpr int kStages = 3;       // feature tiles in the producer -> consumer ring
+constexpr int kCtx = 1;          // tiles the consumers keep in flight (2 = ping-pong; measured slower)
+constexpr uint32_t kFieldTmemCols = 64 * kCtx;
 
 struct FieldPlan {
     uint32_t k0;                 // sigma-net input width = 2L
     uint32_t ws_bytes, wc_bytes; // weight bytes of the two nets
     uint32_t ws_off, wc_off, a0_off, h_off, lv_off, misc_off, total;
-    uint32_t a0_stage;
+    uint32_t a0_stage, h_bytes;
 };
 __host__ __device__ inline FieldPlan field_plan(uint32_t L, uint32_t ns, uint32_t nc) {
     FieldPlan p;
@@ -50,25 +54,40 @@ __host__ __device__ inline FieldPlan field_plan(uint32_t L, uint32_t ns, uint32_
     p.ws_off = 0;
     p.wc_off = p.ws_off + p.ws_bytes;
     p.a0_stage = kTileRows * p.k0 * 2u;
+    p.h_bytes = kTileRows * kFW * 2u;
     p.a0_off = (p.wc_off + p.wc_bytes + 127u) & ~127u;
     p.h_off = p.a0_off + kStages * p.a0_stage;
-    p.lv_off = p.h_off + kTileRows * kFW * 2u;
+    p.lv_off = p.h_off + kCtx * p.h_bytes;
     p.misc_off = p.lv_off + (uint32_t)sizeof(PairLevel) * kFieldMaxLevels;
     p.total = p.misc_off + 128u;
     return p;
 }
 
+// development probes (-DNTX_DEV_PROBES, tools/field_probe.py): cycle accounting of one producer and one consumer warp per CTA
+#ifdef NTX_DEV_PROBES
+__device__ unsigned long long g_probe[8];   // consumer: wait_full, wait_mma, epilogue | - | producer: wait_empty, gather, loads | CTAs
+#define PROBE_DECL unsigned long long pr_t = clock64(), pr_acc[3] = {0, 0, 0};
+#define PROBE_MARK(i) { const unsigned long long n_ = clock64(); pr_acc[i] += n_ - pr_t; pr_t = n_; }
+#define PROBE_FLUSH(base) { for (int i_ = 0; i_ < 3; i_++) atomicAdd(&g_probe[(base) + i_], pr_acc[i_]); }
+#else
+#define PROBE_DECL
+#define PROBE_MARK(i) {}
+#define PROBE_FLUSH(base) {}
+#endif
+
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kConsumerWarps) : "memory"); }
 
-// hidden-layer epilogue (4 consumer warps, warp w owns TMEM lanes 32w..32w+31 = tile rows): four 16-column passes
-// (keeps the consumer inside the kernel's 64-register budget)
-__device__ __forceinline__ void field_hidden_epilogue(uint32_t tmem_base, uint8_t* h_smem, uint32_t warp, uint32_t lane) {
-    const uint32_t row = warp * 32 + lane;
+// hidden-layer epilogue: warp w owns TMEM lanes 32*(w&3).. (= tile rows) and columns 32*(w>>2)..+31: two 16-column passes
+// (the stage chain is latency-bound: splitting a row's 64 columns over two warps halves the dependent instruction chain)
+__device__ __forceinline__ void field_hidden_epilogue(uint32_t tmem_acc, uint8_t* h_smem, uint32_t warp, uint32_t lane) {
+    const uint32_t quarter = warp & 3u, row = quarter * 32 + lane;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const uint32_t col = q * 16;
+    constexpr int kPasses = 16 / kConsumerWarps;             // 16-column passes per warp
+#pragma unroll
+    for (int q = 0; q < kPasses; q++) {
+        const uint32_t col = (warp >> 2) * (16 * kPasses) + q * 16;
         uint32_t v[16];
-        tc::tmem_ld_x16(tmem_base + ((warp * 32u) << 16) + col, v);
+        tc::tmem_ld_x16(tmem_acc + ((quarter * 32u) << 16) + col, v);
         tc::tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 16; j += 8) {
@@ -82,6 +101,26 @@ __device__ __forceinline__ void field_hidden_epilogue(uint32_t tmem_base, uint8_
     }
 }
 
+// consumer stage st (0 .. ns+nc+1) = "MMA st has completed -> epilogue".  Layer table (weights in the order the nets store them):
+//   st = 0          a0 [128 x 2L] . Ws0^T -> 64      hidden epilogue          (issued when the feature tile arrives)
+//   st = 1..ns-1    h . Ws(st)^T          -> 64      hidden epilogue
+//   st = ns         h . Ws_out^T          -> 16      sigma + colour-net input
+//   st = ns+1       h [128 x 32] . Wc0^T  -> 64      hidden epilogue
+//   st = ns+2..ns+nc                      -> 64      hidden epilogue
+//   st = ns+nc+1    h . Wc_out^T          -> 16      rgb
+__device__ __forceinline__ void field_issue_stage(uint32_t st, uint32_t ns, uint32_t nc, uint32_t K0, uint32_t h_addr, uint32_t ws_addr, uint32_t wc_addr,
+                                                  uint32_t tmem_acc) {
+    if (st <= ns) {
+        const uint32_t w = ws_addr + kFW * K0 * 2u + (st - 1) * (kFW * kFW * 2u);
+        issue_layer(h_addr, w, kFW, st == ns ? 16u : (uint32_t)kFW, tmem_acc);
+    } else if (st == ns + 1) {
+        issue_layer(h_addr, wc_addr, kColorIn, kFW, tmem_acc);
+    } else {
+        const uint32_t w = wc_addr + kFW * kColorIn * 2u + (st - ns - 2) * (kFW * kFW * 2u);
+        issue_layer(h_addr, w, kFW, st == ns + nc + 1 ? 16u : (uint32_t)kFW, tmem_acc);
+    }
+}
+
 __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
     const float* __restrict__ xyz, const float* __restrict__ dirs, const float* __restrict__ deltas, const uint32_t M, const float bound,
     const __half* __restrict__ table, const int* __restrict__ offsets, const uint32_t L, const float S, const uint32_t H, const bool align,
@@ -92,23 +131,23 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
     uint8_t* ws_smem = smem + plan.ws_off;
     uint8_t* wc_smem = smem + plan.wc_off;
     uint8_t* a0_smem = smem + plan.a0_off;   // kStages tiles
-    uint8_t* h_smem = smem + plan.h_off;
+    uint8_t* h_smem = smem + plan.h_off;     // kCtx activation buffers
     PairLevel* lv = reinterpret_cast<PairLevel*>(smem + plan.lv_off);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + plan.misc_off);        // [kStages] producers -> consumer
     uint64_t* empty_bar = full_bar + kStages;                                      // [kStages] consumer (MMA completion) -> producers
-    uint64_t* mma_bar = empty_bar + kStages;                                       // layer done -> consumer warps
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+    uint64_t* mma_bar = empty_bar + kStages;                                       // [kCtx] layer done -> consumer warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + kCtx);
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t K0 = plan.k0;
 
-    // ---- one-time setup (all 12 warps) ---------------------------------------------------------------------------
+    // ---- one-time setup (all 16 warps) ---------------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) { tc::mbar_init(&full_bar[s], kTasksPerTile); tc::mbar_init(&empty_bar[s], 1); }
-        tc::mbar_init(mma_bar, 1);
+        for (int c = 0; c < kCtx; c++) tc::mbar_init(&mma_bar[c], 1);
         tc::fence_mbar_init();
     }
-    if (warp == 0) tc::tmem_alloc<64>(tmem_slot);
+    if (warp == 0) tc::tmem_alloc<kFieldTmemCols>(tmem_slot);
     if (tid < L) lv[tid] = make_pair_level(make_level<3>(offsets, tid, S, H, /*gridtype=*/0, align), table);
     {
         const __half* w = w_sigma; uint8_t* dst = ws_smem;
@@ -128,13 +167,14 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
     const uint32_t ntiles = ceil_div<uint32_t>(M, kTileRows);
 
     if (warp >= kConsumerWarps) {
-        // =============================== PRODUCERS: gather + SH =====================================================
+        // =============================== PRODUCERS: gather ===========================================================
         const uint32_t pw = warp - kConsumerWarps;             // 0..11
         const uint32_t p = lane & 1u;                          // which x corner this lane gathers
         const float half_off = align ? 0.0f : 0.5f;
         // GridEncoder.forward: inputs = (inputs + bound) / (2 * bound) (grid.py:143).  torch's CUDA true-division by a Python
         // scalar multiplies by the fp32 reciprocal (BinaryDivTrueKernel.cu), so do exactly that.
         const float inv2b = 1.0f / (2.0f * bound);
+        PROBE_DECL
         for (uint32_t task = pw;; task += kProducerWarps) {
             const uint32_t k = task / kTasksPerTile;            // k-th tile of this CTA
             const uint32_t tile = blockIdx.x + k * gridDim.x;
@@ -154,7 +194,9 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
             const bool oob = (x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1);
             const bool live = !skip && !oob;
             if (!live) { x = 0.f; y = 0.f; z = 0.f; }  // keeps the (discarded) loads of dead lanes in bounds
-            tc::mbar_wait_relaxed(&empty_bar[s], (use & 1u) ^ 1u);   // slot free? (first use of a slot passes immediately)
+            PROBE_MARK(2)
+            tc::mbar_wait_relaxed(&empty_bar[s], (use & 1u) ^ 1u, 256u);   // slot free? (first use of a slot passes immediately)
+            PROBE_MARK(0)
             uint8_t* a0 = a0_smem + s * plan.a0_stage;
             for (uint32_t l0 = 0; l0 < L; l0 += 4) {
                 uint32_t packed[2];
@@ -169,137 +211,151 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
             tc::fence_proxy_async_smem();          // my generic-proxy writes -> visible to the tensor core's async proxy
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&full_bar[s]);
+            PROBE_MARK(1)
         }
+        if (pw == 0 && lane == 0) PROBE_FLUSH(4)
     } else {
-        // =============================== CONSUMERS: the two MLPs =====================================================
-        const uint32_t ws_addr = tc::smem_u32(ws_smem), wc_addr = tc::smem_u32(wc_smem), h_addr = tc::smem_u32(h_smem);
-        uint32_t mma_phase = 0;
-        uint32_t k = 0;
-        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
-            const uint32_t s = k % kStages, use = k / kStages;
-            const uint32_t a0_addr = tc::smem_u32(a0_smem + s * plan.a0_stage);
-            const uint32_t row = warp * 32 + lane;
-            const uint32_t b = tile * kTileRows + row;
-            const bool dead = (b >= M) || (deltas && deltas[(size_t)b * 2] == 0.0f);
-            float dx = 0.f, dy = 0.f, dz = 0.f;     // view direction of this row: its SH basis is evaluated between the two nets
-            if (b < M) { dx = dirs[(size_t)b * 3]; dy = dirs[(size_t)b * 3 + 1]; dz = dirs[(size_t)b * 3 + 2]; }
-
-            tc::mbar_wait(&full_bar[s], use & 1u);
-            tc::tc_fence_after_sync();
+        // =============================== CONSUMERS: the two MLPs, two tiles in flight ================================
+        const uint32_t ws_addr = tc::smem_u32(ws_smem), wc_addr = tc::smem_u32(wc_smem);
+        const uint32_t quarter = warp & 3u, row = quarter * 32 + lane;
+        const bool lead = warp < 4;                      // the warp of a row that handles the 16-wide output layers
+        const bool does_sh = kConsumerWarps == 4 || !lead;   // ... and the one that evaluates SH (its partner, if it has one)
+        const uint32_t nst = ns + nc + 2;
+        uint32_t ph[kCtx] = {};
+        PROBE_DECL
+        for (uint32_t k0 = 0;; k0 += kCtx) {
+            if (blockIdx.x + k0 * gridDim.x >= ntiles) break;
+            uint32_t b[kCtx];
+            bool has[kCtx], dead[kCtx];
+            float dx[kCtx], dy[kCtx], dz[kCtx];   // view direction of this row: its SH basis is evaluated between the two nets
+            // ---------------- take up to kCtx feature tiles and start their first layer --------------------------
+#pragma unroll
+            for (int c = 0; c < kCtx; c++) {
+                const uint32_t k = k0 + c, tile = blockIdx.x + k * gridDim.x;
+                has[c] = tile < ntiles;
+                b[c] = tile * kTileRows + row;
+                dead[c] = true; dx[c] = dy[c] = dz[c] = 0.f;
+                if (!has[c]) continue;
+                const uint32_t s = k % kStages, use = k / kStages;
+                dead[c] = (b[c] >= M) || (deltas && deltas[(size_t)b[c] * 2] == 0.0f);
+                if (b[c] < M) { dx[c] = dirs[(size_t)b[c] * 3]; dy[c] = dirs[(size_t)b[c] * 3 + 1]; dz[c] = dirs[(size_t)b[c] * 3 + 2]; }
+                PROBE_MARK(2)
+                // Only the issuing thread waits for the feature tile: nobody else reads it, and a consumer warp still polling
+                // full_bar[s] after the slot has been released below could see the producers complete the NEXT phase of that
+                // barrier and wait forever on a parity that has come round again.
+                if (warp == 0) { tc::mbar_wait(&full_bar[s], use & 1u); tc::tc_fence_after_sync(); }
+                PROBE_MARK(0)
 #ifdef NTX_DEV_PROBES
-            if (dbg & 2u) {   // producer-only timing: release the slot at once, skip both MLPs
-                if (tid == 0) tc::mbar_arrive(&empty_bar[s]);
-                if (b < M) { st_stream_f32(sigmas + b, 0.f); for (int c = 0; c < 3; c++) st_stream_f32(rgbs + (size_t)b * 3 + c, 0.f); }
-                continue;
-            }
+                if (dbg & 2u) {   // producer-only timing: release the slot at once, skip both MLPs
+                    if (tid == 0) tc::mbar_arrive(&empty_bar[s]);
+                    if (b[c] < M) { st_stream_f32(sigmas + b[c], 0.f); for (int q = 0; q < 3; q++) st_stream_f32(rgbs + (size_t)b[c] * 3 + q, 0.f); }
+                    has[c] = false;
+                    continue;
+                }
 #endif
-            // ---------------- sigma net ------------------------------------------------------------------------
-            if (tid == 0) {
-                issue_layer(a0_addr, ws_addr, K0, kFW, tmem_base);
-                tc::mma_commit(mma_bar);
-                tc::mma_commit(&empty_bar[s]);   // the feature tile is free again as soon as this MMA has read it
-            }
-            tc::mbar_wait(mma_bar, mma_phase); mma_phase ^= 1;
-            tc::tc_fence_after_sync();
-            field_hidden_epilogue(tmem_base, h_smem, warp, lane);
-            tc::fence_proxy_async_smem(); tc::tc_fence_before_sync(); consumer_sync();
-            uint32_t w_off = kFW * K0 * 2u;
-            for (uint32_t j = 0; j + 1 < ns; j++) {
-                if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(h_addr, ws_addr + w_off, kFW, kFW, tmem_base); tc::mma_commit(mma_bar); }
-                tc::mbar_wait(mma_bar, mma_phase); mma_phase ^= 1;
-                tc::tc_fence_after_sync();
-                field_hidden_epilogue(tmem_base, h_smem, warp, lane);
-                tc::fence_proxy_async_smem(); tc::tc_fence_before_sync(); consumer_sync();
-                w_off += kFW * kFW * 2u;
-            }
-            if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(h_addr, ws_addr + w_off, kFW, 16, tmem_base); tc::mma_commit(mma_bar); }
-            tc::mbar_wait(mma_bar, mma_phase); mma_phase ^= 1;
-            tc::tc_fence_after_sync();
-            {
-                uint32_t v[16];
-                tc::tmem_ld_x16(tmem_base + ((warp * 32u) << 16), v);
-                tc::tmem_wait_ld();
-                // h = fp16(W2 . a)   (FFMLP output is fp16); sigma = trunc_exp(h[0]) = exp(float(h[0]))   (network_ff.py:88)
-                uint32_t hb[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) hb[j] = float2_to_half2_bits(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                const float h0 = __low2float(*reinterpret_cast<const __half2*>(&hb[0]));
-                if (b < M) st_stream_f32(sigmas + b, dead ? 0.0f : density_scale * expf(h0));
-                // colour-net input [128 x 32] = SH(dir) ++ h[1..15] ++ 0   (network_ff.py:93-97), built at the start of h_smem: the
-                // hidden activations there are dead (the output-layer MMA has completed), and the colour net's first epilogue
-                // overwrites it only after its MMA has read it.
-                uint4 c2, c3;
-                c2.x = __byte_perm(hb[0], hb[1], 0x5432); c2.y = __byte_perm(hb[1], hb[2], 0x5432);
-                c2.z = __byte_perm(hb[2], hb[3], 0x5432); c2.w = __byte_perm(hb[3], hb[4], 0x5432);
-                c3.x = __byte_perm(hb[4], hb[5], 0x5432); c3.y = __byte_perm(hb[5], hb[6], 0x5432);
-                c3.z = __byte_perm(hb[6], hb[7], 0x5432); c3.w = __byte_perm(hb[7], 0u, 0x5432);
-                *reinterpret_cast<uint4*>(h_smem + kmajor_chunk_off(row, 2, kColorIn)) = c2;
-                *reinterpret_cast<uint4*>(h_smem + kmajor_chunk_off(row, 3, kColorIn)) = c3;
-                // SH of the view direction (fp32, rounded to fp16 when it enters the fp16 MLP)
-                float sh[16];
-                sh_basis<4, false>(dx, dy, dz, sh, nullptr, nullptr, nullptr);
-                uint4 s0, s1;
-                s0.x = float2_to_half2_bits(sh[0], sh[1]); s0.y = float2_to_half2_bits(sh[2], sh[3]);
-                s0.z = float2_to_half2_bits(sh[4], sh[5]); s0.w = float2_to_half2_bits(sh[6], sh[7]);
-                s1.x = float2_to_half2_bits(sh[8], sh[9]); s1.y = float2_to_half2_bits(sh[10], sh[11]);
-                s1.z = float2_to_half2_bits(sh[12], sh[13]); s1.w = float2_to_half2_bits(sh[14], sh[15]);
-                *reinterpret_cast<uint4*>(h_smem + kmajor_chunk_off(row, 0, kColorIn)) = s0;
-                *reinterpret_cast<uint4*>(h_smem + kmajor_chunk_off(row, 1, kColorIn)) = s1;
-            }
-            tc::fence_proxy_async_smem(); tc::tc_fence_before_sync(); consumer_sync();
-
-            // ---------------- colour net -----------------------------------------------------------------------
-            if (tid == 0) {
-                tc::tc_fence_after_sync();
-                issue_layer(h_addr, wc_addr, kColorIn, kFW, tmem_base);
-                tc::mma_commit(mma_bar);
-            }
-            tc::mbar_wait(mma_bar, mma_phase); mma_phase ^= 1;
-            tc::tc_fence_after_sync();
-            field_hidden_epilogue(tmem_base, h_smem, warp, lane);
-            tc::fence_proxy_async_smem(); tc::tc_fence_before_sync(); consumer_sync();
-            w_off = kFW * kColorIn * 2u;
-            for (uint32_t j = 0; j + 1 < nc; j++) {
-                if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(h_addr, wc_addr + w_off, kFW, kFW, tmem_base); tc::mma_commit(mma_bar); }
-                tc::mbar_wait(mma_bar, mma_phase); mma_phase ^= 1;
-                tc::tc_fence_after_sync();
-                field_hidden_epilogue(tmem_base, h_smem, warp, lane);
-                tc::fence_proxy_async_smem(); tc::tc_fence_before_sync(); consumer_sync();
-                w_off += kFW * kFW * 2u;
-            }
-            if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(h_addr, wc_addr + w_off, kFW, 16, tmem_base); tc::mma_commit(mma_bar); }
-            tc::mbar_wait(mma_bar, mma_phase); mma_phase ^= 1;
-            tc::tc_fence_after_sync();
-            {
-                uint32_t v[8];
-                tc::tmem_ld_x8(tmem_base + ((warp * 32u) << 16), v);
-                tc::tmem_wait_ld();
-                if (b < M) {
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        // rgb = sigmoid(h) evaluated on the fp16 output in fp32 and rounded back to fp16 (torch.sigmoid on a half tensor)
-                        const float hc = __half2float(__float2half_rn(__uint_as_float(v[c])));
-                        const float sg = 1.0f / (1.0f + expf(-hc));
-                        st_stream_f32(rgbs + (size_t)b * 3 + c, dead ? 0.0f : __half2float(__float2half_rn(sg)));
-                    }
+                if (warp == 0 && tc::elect_one()) {
+                    issue_layer(tc::smem_u32(a0_smem + s * plan.a0_stage), ws_addr, K0, kFW, tmem_base + c * 64u);
+                    tc::mma_commit(&mma_bar[c]);
+                    tc::mma_commit(&empty_bar[s]);   // the feature tile is free again as soon as this MMA has read it
                 }
             }
-            tc::tc_fence_before_sync();
-            consumer_sync();   // TMEM accumulator is reused by the next tile's first MMA
+            // ---------------- the stages, alternating between the tiles ---------------------------------------------
+            for (uint32_t st = 0; st < nst; st++) {
+#pragma unroll
+                for (int c = 0; c < kCtx; c++) {
+                    if (!has[c]) continue;
+                    uint8_t* h = h_smem + c * plan.h_bytes;
+                    const uint32_t acc = tmem_base + c * 64u;
+                    tc::mbar_wait(&mma_bar[c], ph[c]); ph[c] ^= 1;
+                    PROBE_MARK(1)
+                    tc::tc_fence_after_sync();
+                    if (st == ns && does_sh) {
+                        // SH of the view direction (fp32, rounded to fp16 when it enters the fp16 MLP): columns 0..15 of the colour input
+                        uint8_t* hc = h;
+                        float sh[16];
+                        sh_basis<4, false>(dx[c], dy[c], dz[c], sh, nullptr, nullptr, nullptr);
+                        uint4 s0, s1;
+                        s0.x = float2_to_half2_bits(sh[0], sh[1]); s0.y = float2_to_half2_bits(sh[2], sh[3]);
+                        s0.z = float2_to_half2_bits(sh[4], sh[5]); s0.w = float2_to_half2_bits(sh[6], sh[7]);
+                        s1.x = float2_to_half2_bits(sh[8], sh[9]); s1.y = float2_to_half2_bits(sh[10], sh[11]);
+                        s1.z = float2_to_half2_bits(sh[12], sh[13]); s1.w = float2_to_half2_bits(sh[14], sh[15]);
+                        *reinterpret_cast<uint4*>(hc + kmajor_chunk_off(row, 0, kColorIn)) = s0;
+                        *reinterpret_cast<uint4*>(hc + kmajor_chunk_off(row, 1, kColorIn)) = s1;
+                    }
+                    if (st == ns && lead) {
+                        uint32_t v[16];
+                        tc::tmem_ld_x16(acc + ((quarter * 32u) << 16), v);
+                        tc::tmem_wait_ld();
+                        // h = fp16(W2 . a)   (FFMLP output is fp16); sigma = trunc_exp(h[0]) = exp(float(h[0]))   (network_ff.py:88)
+                        uint32_t hb[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) hb[j] = float2_to_half2_bits(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                        const float h0 = __low2float(*reinterpret_cast<const __half2*>(&hb[0]));
+                        if (b[c] < M) st_stream_f32(sigmas + b[c], dead[c] ? 0.0f : density_scale * expf(h0));
+                        // colour-net input [128 x 32] = SH(dir) ++ h[1..15] ++ 0   (network_ff.py:93-97), built at the start of this
+                        // tile's activation buffer: the hidden activations there are dead (the output-layer MMA has completed),
+                        // and the colour net's first epilogue overwrites it only after its MMA has read it.
+                        uint4 c2, c3;
+                        c2.x = __byte_perm(hb[0], hb[1], 0x5432); c2.y = __byte_perm(hb[1], hb[2], 0x5432);
+                        c2.z = __byte_perm(hb[2], hb[3], 0x5432); c2.w = __byte_perm(hb[3], hb[4], 0x5432);
+                        c3.x = __byte_perm(hb[4], hb[5], 0x5432); c3.y = __byte_perm(hb[5], hb[6], 0x5432);
+                        c3.z = __byte_perm(hb[6], hb[7], 0x5432); c3.w = __byte_perm(hb[7], 0u, 0x5432);
+                        *reinterpret_cast<uint4*>(h + kmajor_chunk_off(row, 2, kColorIn)) = c2;
+                        *reinterpret_cast<uint4*>(h + kmajor_chunk_off(row, 3, kColorIn)) = c3;
+                    } else if (st == ns) {
+                        // (partner warp of an 8-warp consumer group: SH only)
+                    } else if (st + 1 == nst) {
+                        uint32_t v[8];
+                        if (lead) { tc::tmem_ld_x8(acc + ((quarter * 32u) << 16), v); tc::tmem_wait_ld(); }
+                        if (lead && b[c] < M) {
+#pragma unroll
+                            for (int q = 0; q < 3; q++) {
+                                // rgb = sigmoid(h) evaluated on the fp16 output in fp32 and rounded back to fp16 (torch.sigmoid on a half tensor)
+                                const float hc = __half2float(__float2half_rn(__uint_as_float(v[q])));
+                                const float sg = 1.0f / (1.0f + expf(-hc));
+                                st_stream_f32(rgbs + (size_t)b[c] * 3 + q, dead[c] ? 0.0f : __half2float(__float2half_rn(sg)));
+                            }
+                        }
+                    } else {
+                        field_hidden_epilogue(acc, h, warp, lane);
+                    }
+                    // epilogue done by all four warps: this tile's next layer may read the activation buffer and overwrite the
+                    // accumulator (after the last stage: the next tile in this context may)
+                    tc::fence_proxy_async_smem(); tc::tc_fence_before_sync(); consumer_sync();
+                    if (st + 1 < nst && warp == 0 && tc::elect_one()) {
+                        tc::tc_fence_after_sync();
+                        field_issue_stage(st + 1, ns, nc, K0, tc::smem_u32(h), ws_addr, wc_addr, acc);
+                        tc::mma_commit(&mma_bar[c]);
+                    }
+                    PROBE_MARK(2)
+                }
+            }
         }
+        if (tid == 0) PROBE_FLUSH(0)
     }
 
     tc::tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc<64>(tmem_base);
+    if (warp == 0) tc::tmem_dealloc<kFieldTmemCols>(tmem_base);
+#ifdef NTX_DEV_PROBES
+    if (tid == 0) atomicAdd(&g_probe[7], 1ull);
+#endif
 }
 
 }  // namespace ntx
 
 using namespace ntx;
 
-// development probes (only in builds with -DNTX_DEV_PROBES; tools/field_probe.py): bit 0 = producers skip the gather,
-// bit 1 = consumers skip the MLPs.  Product builds always pass 0 and the branches do not exist.
+// development probes (only in builds with -DNTX_DEV_PROBES; tools/field_probe.py): NTX_FIELD_DEBUG bit 0 = producers skip the
+// gather, bit 1 = consumers skip the MLPs; ntx_dev_probe_read returns the cycle accounting.  Product builds always pass 0
+// and the branches do not exist.
+#ifdef NTX_DEV_PROBES
+extern "C" int ntx_dev_probe_read(unsigned long long* out8, int reset) {
+    if (cudaMemcpyFromSymbol(out8, g_probe, sizeof(unsigned long long) * 8) != cudaSuccess) return NTX_ERR_CUDA;
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_probe, z, sizeof(z)); }
+    return NTX_OK;
+}
+#endif
 static uint32_t dev_probe_flags() {
 #ifdef NTX_DEV_PROBES
     const char* e = getenv("NTX_FIELD_DEBUG");
@@ -331,7 +387,7 @@ extern "C" int ntx_ngp_field_forward(const float* xyz, const float* dirs, const 
         occ = 0;
     }
     if (!occ) {
-        occ = resident_ctas_per_sm((const void*)ngp_field_kernel, kFieldThreads, plan.total, 64);
+        occ = resident_ctas_per_sm((const void*)ngp_field_kernel, kFieldThreads, plan.total, kFieldTmemCols);
         if (tunables().field_ctas > 0) occ = std::min(occ, tunables().field_ctas);
     }
     const int sms = device_sm_count();

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fused_kernel(const __half* __
         __syncthreads();
 
         // first layer: [128 x in_dim] . W0^T
-        if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(a0_addr, w_addr, in_dim, WIDTH, tmem_base); tc::mma_commit(bar); }
+        if (warp == 0 && tc::elect_one()) { tc::tc_fence_after_sync(); issue_layer(a0_addr, w_addr, in_dim, WIDTH, tmem_base); tc::mma_commit(bar); }
         tc::mbar_wait(bar, phase); phase ^= 1;
         tc::tc_fence_after_sync();
         hidden_epilogue<WIDTH>(tmem_base, h_smem, act, TRAIN ? fwd_buf + ((size_t)0 * B + row0) * WIDTH : nullptr, rows_valid);
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fused_kernel(const __half* __
 
         // hidden layers, in place: the MMA that read h_smem has completed before the epilogue overwrites it
         for (uint32_t k = 0; k < n_hidden; k++) {
-            if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(h_addr, w_hidden_addr + k * WIDTH * WIDTH * 2u, WIDTH, WIDTH, tmem_base); tc::mma_commit(bar); }
+            if (warp == 0 && tc::elect_one()) { tc::tc_fence_after_sync(); issue_layer(h_addr, w_hidden_addr + k * WIDTH * WIDTH * 2u, WIDTH, WIDTH, tmem_base); tc::mma_commit(bar); }
             tc::mbar_wait(bar, phase); phase ^= 1;
             tc::tc_fence_after_sync();
             hidden_epilogue<WIDTH>(tmem_base, h_smem, act, TRAIN ? fwd_buf + ((size_t)(k + 1) * B + row0) * WIDTH : nullptr, rows_valid);
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fused_kernel(const __half* __
         }
 
         // output layer: N = 16 (ffmlp.py:118 pads output_dim to 16)
-        if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(h_addr, w_last_addr, WIDTH, 16, tmem_base); tc::mma_commit(bar); }
+        if (warp == 0 && tc::elect_one()) { tc::tc_fence_after_sync(); issue_layer(h_addr, w_last_addr, WIDTH, 16, tmem_base); tc::mma_commit(bar); }
         tc::mbar_wait(bar, phase); phase ^= 1;
         tc::tc_fence_after_sync();
         if (warp < 4) {

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kBwdThreads) mlp_dgrad_kernel(const __half* __
         __syncthreads();
 
         // through the output layer: dH = (G . W_last) * act'(fwd[n-1])      (ffmlp.cu:452-500)
-        if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(g_addr, w_addr, 16, WIDTH, tmem_base); tc::mma_commit(bar); }
+        if (warp == 0 && tc::elect_one()) { tc::tc_fence_after_sync(); issue_layer(g_addr, w_addr, 16, WIDTH, tmem_base); tc::mma_commit(bar); }
         tc::mbar_wait(bar, phase); phase ^= 1;
         tc::tc_fence_after_sync();
         dgrad_epilogue<WIDTH>(tmem_base, h_smem, act, fwd_buf + ((size_t)(num_layers - 1) * B + row0) * WIDTH, bwd_buf + ((size_t)0 * B + row0) * WIDTH, rows_valid);
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kBwdThreads) mlp_dgrad_kernel(const __half* __
         // hidden layers, last to first (ffmlp.cu:508-510)
         for (uint32_t k = 0; k < n_hidden; k++) {
             const uint32_t j = n_hidden - 1 - k;   // hidden matrix index
-            if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(h_addr, wh_addr + j * WIDTH * WIDTH * 2u, WIDTH, WIDTH, tmem_base); tc::mma_commit(bar); }
+            if (warp == 0 && tc::elect_one()) { tc::tc_fence_after_sync(); issue_layer(h_addr, wh_addr + j * WIDTH * WIDTH * 2u, WIDTH, WIDTH, tmem_base); tc::mma_commit(bar); }
             tc::mbar_wait(bar, phase); phase ^= 1;
             tc::tc_fence_after_sync();
             dgrad_epilogue<WIDTH>(tmem_base, h_smem, act, fwd_buf + ((size_t)j * B + row0) * WIDTH, bwd_buf + ((size_t)(k + 1) * B + row0) * WIDTH, rows_valid);
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kBwdThreads) mlp_dgrad_kernel(const __half* __
         if (grad_in) {
             for (uint32_t n0 = 0; n0 < in_dim; n0 += TM_COLS) {
                 const uint32_t ncols = min(TM_COLS, in_dim - n0);
-                if (tid == 0) { tc::tc_fence_after_sync(); issue_layer(h_addr, w0_addr + (n0 >> 3) * (WIDTH * 16u), WIDTH, ncols, tmem_base); tc::mma_commit(bar); }
+                if (warp == 0 && tc::elect_one()) { tc::tc_fence_after_sync(); issue_layer(h_addr, w0_addr + (n0 >> 3) * (WIDTH * 16u), WIDTH, ncols, tmem_base); tc::mma_commit(bar); }
                 tc::mbar_wait(bar, phase); phase ^= 1;
                 tc::tc_fence_after_sync();
                 if (warp < 4) {

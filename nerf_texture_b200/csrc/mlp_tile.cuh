@@ -72,14 +72,15 @@ __device__ __forceinline__ float mlp_activation(uint32_t act, float x) {
 }
 __device__ __forceinline__ uint32_t act_pack2(uint32_t act, uint32_t a_bits, uint32_t b_bits) {
     // accumulator (fp32) -> fp16 -> activation in fp32 -> fp16, two lanes at a time
-    const __half2 h = __floats2half2_rn(__uint_as_float(a_bits), __uint_as_float(b_bits));
     if (act == 0) {
-        const __half2 z = __floats2half2_rn(0.f, 0.f);
-        // the reference writes ReLU as x * (x > 0) (NaN-propagating; negative x gives -0).  max(x, 0) with NaN propagation is
-        // one instruction instead of two and differs only in the sign of that zero, which nothing downstream can observe
-        const __half2 r = __hmax2_nan(h, z);
-        return *reinterpret_cast<const uint32_t*>(&r);
+        // the reference rounds to fp16 and then applies ReLU as x * (x > 0) (NaN-propagating; negative x gives -0).
+        // cvt.rn.relu does clamp + round + pack in ONE instruction (F2FP.RELU); clamping before rounding gives the same
+        // value, NaN still propagates, and only the sign of a zero differs, which nothing downstream can observe.
+        uint32_t r;
+        asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(b_bits)), "f"(__uint_as_float(a_bits)));
+        return r;
     }
+    const __half2 h = __floats2half2_rn(__uint_as_float(a_bits), __uint_as_float(b_bits));
     if (act >= 6) return *reinterpret_cast<const uint32_t*>(&h);
     const float2 f = __half22float2(h);
     return float2_to_half2_bits(mlp_activation(act, f.x), mlp_activation(act, f.y));

@@ -10,6 +10,15 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp (call it from warp-uniform code only).  Unlike `threadIdx.x == 0`, the compiler knows that
+// exactly one lane runs the guarded code, so tcgen05.mma/commit operands go straight into uniform registers; a plain
+// `if (tid == 0)` makes it wrap every UTCHMMA in a ~20-instruction elect/R2UR "waterfall" loop (seen in SASS).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -32,18 +41,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-// same for waits that are not latency-critical (a producer waiting for a free slot): the thread is suspended for up to
-// ~1 us per poll instead of burning issue slots the working warps of the SM need
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+// same for waits that are not latency-critical (a producer waiting for a free slot): sleep between polls instead of burning
+// issue slots — a spinning warp competes with the working warps of its scheduler (ncu: 21 % of all issued instructions
+// were this loop, and the consumer warps it was waiting for ran at half speed)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t sleep_ns) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
-    for (uint32_t spin = 0; !done; ++spin) {
+    for (uint32_t spin = 0;; ++spin) {
         asm volatile(
             "{\n .reg .pred p;\n"
-            " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
             " selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(done) : "r"(addr), "r"(parity), "r"(1000u) : "memory");
-        if (spin > (1u << 22)) __trap();
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        asm volatile("nanosleep.u32 %0;" ::"r"(sleep_ns));
+        if (spin > (1u << 24)) __trap();
     }
 }
 
