@@ -134,7 +134,7 @@ int ntx_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, con
                    const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
                    const uint8_t* grid, const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
                    uint32_t perturb, int zero_fill, uint32_t M_padded, const uint8_t* occupancy_mip /* nullable */, ntx_stream_t stream);
-/* Optional accelerator of march_rays: a conservative (dilated) 8x8x8-cell mip of the occupancy bit-field.  With it the marcher
+/* Optional accelerator of march_rays: a conservative (dilated) 4x4x4-cell mip of the occupancy bit-field.  With it the marcher
  * stops walking a ray through empty space as soon as no occupied voxel can be reached any more; the emitted samples are
  * unchanged (such a ray emits nothing further and is marked dead by composite_rays whatever t it stops at).
  * mip: ntx_occupancy_mip_bytes(C,H) bytes; rebuild whenever the bit-field changes.  H must be a power of two >= 16. */
@@ -159,6 +159,29 @@ int ntx_ngp_field_forward(const float* xyz, const float* dirs, const float* delt
                           const void* embeddings_f16, const int* offsets, uint32_t L, float S, uint32_t H,
                           int align_corners, const void* w_sigma_f16, const void* w_color_f16, float density_scale,
                           float* sigmas, float* rgbs, ntx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ whole frame
+ * The inference branch of NeRFRenderer.run_cuda (nerf/renderer.py:436-489) as ONE call: near_far_from_aabb, then per
+ * iteration compact_rays -> march_rays -> field -> composite_rays, with exactly the reference's bookkeeping
+ * (n_step = clamp(N // n_alive, 1, 8), samples padded to 128, step += n_step, stop at n_alive == 0 or step >= max_steps).
+ * The reference reads n_alive back with a blocking .item() every iteration (renderer.py:469); here the loop state lives on
+ * the device (the kernels read n_alive / n_step from it), grids are sized from a bound that lags two iterations behind
+ * through a pinned host mailbox, and the launching thread never lets the stream run dry.  Results are bit-identical to
+ * calling the individual entry points in the reference's order.
+ *   rays_o, rays_d [N,3] f32; aabb [6] f32 (device); grid = density bit-field; occupancy_mip nullable (ntx_build_occupancy_mip)
+ *   weights_sum [N], depth [N], image [N,3] f32: overwritten (image WITHOUT the background term, like composite_rays)
+ *   workspace: ntx_render_rays_workspace_bytes(N) bytes of device memory, 256-byte aligned
+ *   host_mailbox: max_steps + 1 ints of pinned, device-mapped host memory (cudaHostAlloc / torch pin_memory)
+ *   sample_counter: nullable device counter, incremented by the number of samples marched (statistics)
+ *   iterations_out: nullable host pointer, number of loop iterations that had rays alive
+ * Not re-entrant (uses one set of events per process). */
+size_t ntx_render_rays_workspace_bytes(uint32_t N);
+int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const float* aabb, float min_near, float bound,
+                    float dt_gamma, uint32_t max_steps, uint32_t perturb, uint32_t C, uint32_t H, const uint8_t* grid,
+                    const uint8_t* occupancy_mip, const void* embeddings_f16, const int* offsets, uint32_t L, float S,
+                    uint32_t base_resolution, int align_corners, const void* w_sigma_f16, const void* w_color_f16,
+                    float density_scale, float* weights_sum, float* depth, float* image, void* workspace,
+                    int* host_mailbox, unsigned long long* sample_counter, uint32_t* iterations_out, ntx_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -68,6 +68,11 @@ inline int resident_ctas_per_sm(const void* func, int threads, size_t dyn_smem, 
     n = std::min(n, 32);
     return std::max(n, 1);
 }
+// field.cu: the fused field kernel, callable from the device-driven frame loop in raymarch.cu
+int launch_ngp_field(const float* xyz, const float* dirs, const float* deltas, uint32_t M, const int* M_dev, float bound, const void* embeddings_f16,
+                     const int* offsets, uint32_t L, float S, uint32_t H, int align_corners, const void* w_sigma_f16, const void* w_color_f16,
+                     float density_scale, float* sigmas, float* rgbs, cudaStream_t stream);
+
 inline int device_sm_count() {
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);

@@ -122,11 +122,12 @@ __device__ __forceinline__ void field_issue_stage(uint32_t st, uint32_t ns, uint
 }
 
 __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
-    const float* __restrict__ xyz, const float* __restrict__ dirs, const float* __restrict__ deltas, const uint32_t M, const float bound,
-    const __half* __restrict__ table, const int* __restrict__ offsets, const uint32_t L, const float S, const uint32_t H, const bool align,
+    const float* __restrict__ xyz, const float* __restrict__ dirs, const float* __restrict__ deltas, const uint32_t M_arg, const int* __restrict__ M_dev,
+    const float bound, const __half* __restrict__ table, const int* __restrict__ offsets, const uint32_t L, const float S, const uint32_t H, const bool align,
     const __half* __restrict__ w_sigma, const __half* __restrict__ w_color, const uint32_t ns, const uint32_t nc, const float density_scale,
     float* __restrict__ sigmas, float* __restrict__ rgbs, const uint32_t dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t M = M_dev ? (uint32_t)*M_dev : M_arg;     // device-driven frames: the sample count of this launch lives on the device
     const FieldPlan plan = field_plan(L, ns, nc);
     uint8_t* ws_smem = smem + plan.ws_off;
     uint8_t* wc_smem = smem + plan.wc_off;
@@ -368,6 +369,14 @@ static uint32_t dev_probe_flags() {
 extern "C" int ntx_ngp_field_forward(const float* xyz, const float* dirs, const float* deltas, uint32_t M, float bound, const void* embeddings_f16,
                                      const int* offsets, uint32_t L, float S, uint32_t H, int align_corners, const void* w_sigma_f16,
                                      const void* w_color_f16, float density_scale, float* sigmas, float* rgbs, ntx_stream_t stream) {
+    return launch_ngp_field(xyz, dirs, deltas, M, nullptr, bound, embeddings_f16, offsets, L, S, H, align_corners, w_sigma_f16, w_color_f16, density_scale, sigmas,
+                            rgbs, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// M = upper bound of the sample count (sizes the grid); M_dev (nullable, device) = the actual count, read by the kernel
+int ntx::launch_ngp_field(const float* xyz, const float* dirs, const float* deltas, uint32_t M, const int* M_dev, float bound, const void* embeddings_f16,
+                          const int* offsets, uint32_t L, float S, uint32_t H, int align_corners, const void* w_sigma_f16, const void* w_color_f16,
+                          float density_scale, float* sigmas, float* rgbs, cudaStream_t stream) {
     NTX_REQUIRE(xyz && dirs && embeddings_f16 && offsets && w_sigma_f16 && w_color_f16 && sigmas && rgbs, NTX_ERR_INVALID_ARGUMENT, "ngp_field_forward: null pointer");
     NTX_REQUIRE(L >= 8 && L <= kFieldMaxLevels && L % 8 == 0, NTX_ERR_UNSUPPORTED, "ngp_field_forward: num_levels must be 8, 16, 24 or 32 (got %u)", L);
     NTX_REQUIRE(((uintptr_t)w_sigma_f16 & 15) == 0 && ((uintptr_t)w_color_f16 & 15) == 0, NTX_ERR_INVALID_ARGUMENT, "ngp_field_forward: weights must be 16-byte aligned");
@@ -393,8 +402,8 @@ extern "C" int ntx_ngp_field_forward(const float* xyz, const float* dirs, const 
     const int sms = device_sm_count();
     const uint32_t ntiles = ceil_div<uint32_t>(M, kTileRows);
     const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)(occ * sms));
-    ngp_field_kernel<<<grid, kFieldThreads, plan.total, reinterpret_cast<cudaStream_t>(stream)>>>(
-        xyz, dirs, deltas, M, bound, static_cast<const __half*>(embeddings_f16), offsets, L, S, H, align_corners != 0,
+    ngp_field_kernel<<<grid, kFieldThreads, plan.total, stream>>>(
+        xyz, dirs, deltas, M, M_dev, bound, static_cast<const __half*>(embeddings_f16), offsets, L, S, H, align_corners != 0,
         static_cast<const __half*>(w_sigma_f16), static_cast<const __half*>(w_color_f16), ns, nc, density_scale, sigmas, rgbs, dev_probe_flags());
     return check_launch("ngp_field_forward");
 }

@@ -674,12 +674,18 @@ __device__ __forceinline__ void block_copy_out(float* __restrict__ dst, const fl
     for (uint32_t i = (nvec << 2) + threadIdx.x; i < nfloats; i += blockDim.x) dst[i] = src[i];
 }
 
+// Device-driven frames (ntx_render_rays): n_alive / n_step / M_padded of an iteration are only known on the device.  The
+// kernels of the inference loop then take them from a FrameState and the by-value arguments are just the launch bound.
+struct FrameState { int n_alive, n_step, m_padded, step; };
+
 __global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
-    const uint32_t n_alive, const uint32_t n_step, const int* __restrict__ rays_alive, const float* __restrict__ rays_t, const float* __restrict__ rays_o,
+    uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_alive, const float* __restrict__ rays_t, const float* __restrict__ rays_o,
     const float* __restrict__ rays_d, const float bound, const float dt_gamma, const uint32_t max_steps, const uint32_t C, const uint32_t H,
     const uint8_t* __restrict__ grid, const float* __restrict__ nears, const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs,
-    float* __restrict__ deltas, const uint32_t perturb, const uint32_t M_padded, const uint8_t* __restrict__ coarse) {
+    float* __restrict__ deltas, const uint32_t perturb, uint32_t M_padded, const uint8_t* __restrict__ coarse, const FrameState* __restrict__ state,
+    unsigned long long* __restrict__ sample_counter) {
     extern __shared__ __align__(16) float stage[];          // [128*n_step*3] xyz | [128*n_step*3] dir | [128*n_step*2] delta
+    if (state) { n_alive = (uint32_t)state->n_alive; n_step = (uint32_t)state->n_step; M_padded = (uint32_t)state->m_padded; }
     float* sx = stage;
     float* sd = stage + kMarchThreads * n_step * 3;
     float* sl = sd + kMarchThreads * n_step * 3;
@@ -766,6 +772,15 @@ __global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
                 if (!maybe_occupied_ahead(r, p, coarse, t, far)) break;
             }
         }
+        if (sample_counter) {                                // bench / statistics only: samples emitted in this launch
+            if (__activemask() == 0xffffffffu) {             // full warp: one atomic per warp
+                uint32_t cnt = step;
+                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                if ((threadIdx.x & 31) == 0) atomicAdd(sample_counter, (unsigned long long)cnt);
+            } else {
+                atomicAdd(sample_counter, (unsigned long long)step);
+            }
+        }
         for (; step < n_step; step++) {                      // unused slots: zero (delta == 0 is composite_rays' stop sentinel)
             px[0] = 0; px[1] = 0; px[2] = 0; pd[0] = 0; pd[1] = 0; pd[2] = 0; pl[0] = 0; pl[1] = 0;
             px += 3; pd += 3; pl += 2;
@@ -780,10 +795,11 @@ __global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
 }
 
 // raymarching.cu:1021-1104
-__global__ void __launch_bounds__(128) composite_rays_kernel(const uint32_t n_alive, const uint32_t n_step, const int* __restrict__ rays_alive,
+__global__ void __launch_bounds__(128) composite_rays_kernel(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_alive,
                                                              float* __restrict__ rays_t, const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                                                              const float* __restrict__ deltas, float* __restrict__ weights_sum, float* __restrict__ depth,
-                                                             float* __restrict__ image) {
+                                                             float* __restrict__ image, const FrameState* __restrict__ state) {
+    if (state) { n_alive = (uint32_t)state->n_alive; n_step = (uint32_t)state->n_step; }
     const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
     if (n >= n_alive) return;
     const int index = rays_alive[n];
@@ -813,9 +829,14 @@ __global__ void __launch_bounds__(128) composite_rays_kernel(const uint32_t n_al
 constexpr int kCompactThreads = 256;
 constexpr int kCompactItems = 4;
 
-__global__ void __launch_bounds__(kCompactThreads) compact_rays_kernel(const uint32_t n_alive, int* __restrict__ rays_alive, const int* __restrict__ rays_alive_old,
+// Device-driven mode (state_in != nullptr): the number of rays to compact comes from state_in, the result goes to state_out
+// together with the next iteration's n_step / padded sample count / step counter (the bookkeeping of renderer.py:456-475),
+// and to a pinned host mailbox the launching thread reads a few iterations later.
+__global__ void __launch_bounds__(kCompactThreads) compact_rays_kernel(uint32_t n_alive, int* __restrict__ rays_alive, const int* __restrict__ rays_alive_old,
                                                                        float* __restrict__ rays_t, const float* __restrict__ rays_t_old, int* __restrict__ alive_counter,
-                                                                       ScanWS* ws) {
+                                                                       ScanWS* ws, const FrameState* __restrict__ state_in, FrameState* __restrict__ state_out,
+                                                                       const uint32_t n_rays, const uint32_t max_steps, volatile int* host_mailbox) {
+    if (state_in) n_alive = (uint32_t)state_in->n_alive;
     __shared__ uint32_t s_ticket;
     __shared__ uint32_t s_warp[33];
     __shared__ unsigned long long s_bcast;
@@ -835,10 +856,24 @@ __global__ void __launch_bounds__(kCompactThreads) compact_rays_kernel(const uin
     }
     uint32_t block_total;
     const uint32_t local = block_exclusive_scan(cnt, block_total, s_warp);
-    const unsigned long long base = (ticket == 0) ? (unsigned long long)(uint32_t)alive_counter[0] : 0ull;
+    const unsigned long long base = (ticket == 0 && !state_in) ? (unsigned long long)(uint32_t)alive_counter[0] : 0ull;
     const unsigned long long excl = chained_prefix(ws, ticket, block_total, base, &s_bcast);
     const uint32_t nblocks = gridDim.x;
-    if (ticket == nblocks - 1 && threadIdx.x == 0) alive_counter[0] = (int)(uint32_t)(excl + block_total);
+    if (ticket == nblocks - 1 && threadIdx.x == 0) {
+        const uint32_t total = (uint32_t)(excl + block_total);
+        if (state_in) {
+            FrameState s;
+            s.step = state_in->step + state_in->n_step;                       // step += n_step   (renderer.py:475)
+            s.n_alive = ((uint32_t)s.step < max_steps) ? (int)total : 0;       // while step < max_steps
+            s.n_step = s.n_alive ? (int)max(min(n_rays / (uint32_t)s.n_alive, 8u), 1u) : 0;   // renderer.py:464
+            const uint32_t m = (uint32_t)s.n_alive * (uint32_t)s.n_step;
+            s.m_padded = s.n_alive ? (int)(m + 128u - (m % 128u)) : 0;         // raymarching.py:386-387 (align = 128)
+            *state_out = s;
+            if (host_mailbox) { *host_mailbox = s.n_alive; __threadfence_system(); }
+        } else {
+            alive_counter[0] = (int)total;
+        }
+    }
     uint32_t dst = (uint32_t)excl + local;
 #pragma unroll
     for (int i = 0; i < kCompactItems; i++) {
@@ -941,7 +976,7 @@ extern "C" int ntx_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays
         const size_t smem = (size_t)kMarchThreads * n_step * 8 * sizeof(float);
         march_rays_staged_kernel<<<ceil_div<uint32_t>(threads, kMarchThreads), kMarchThreads, smem, ST(stream)>>>(
             n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs, dirs, deltas, perturb, M_padded,
-            occupancy_mip);
+            occupancy_mip, nullptr, nullptr);
         return check_launch("march_rays");
     }
     march_rays_kernel<<<ceil_div<uint32_t>(threads, 128), 128, 0, ST(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid,
@@ -968,7 +1003,8 @@ extern "C" int ntx_composite_rays(uint32_t n_alive, uint32_t n_step, const int* 
                                   float* weights_sum, float* depth, float* image, ntx_stream_t stream) {
     NTX_REQUIRE(rays_alive && rays_t && sigmas && rgbs && deltas && weights_sum && depth && image, NTX_ERR_INVALID_ARGUMENT, "composite_rays: null pointer");
     if (n_alive == 0) return NTX_OK;
-    composite_rays_kernel<<<ceil_div<uint32_t>(n_alive, 128), 128, 0, ST(stream)>>>(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image);
+    composite_rays_kernel<<<ceil_div<uint32_t>(n_alive, 128), 128, 0, ST(stream)>>>(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image,
+                                                                                    nullptr);
     return check_launch("composite_rays");
 }
 
@@ -981,6 +1017,122 @@ extern "C" int ntx_compact_rays(uint32_t n_alive, int* rays_alive, const int* ra
     if (n_alive == 0) return NTX_OK;
     compact_rays_kernel<<<ceil_div<uint32_t>(n_alive, kCompactThreads * kCompactItems), kCompactThreads, 0, ST(stream)>>>(n_alive, rays_alive, rays_alive_old, rays_t,
                                                                                                                          rays_t_old, alive_counter,
-                                                                                                                         static_cast<ScanWS*>(workspace));
+                                                                                                                         static_cast<ScanWS*>(workspace), nullptr, nullptr,
+                                                                                                                         0, 0, nullptr);
     return check_launch("compact_rays");
+}
+
+// ---------------------------------------------------------------------------------------------------- device-driven frame
+namespace ntx {
+__global__ void __launch_bounds__(256) frame_init_kernel(const uint32_t N, const float* __restrict__ nears, int* __restrict__ rays_alive, float* __restrict__ rays_t,
+                                                         FrameState* __restrict__ state, volatile int* host_mailbox) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < N) { rays_alive[n] = (int)n; rays_t[n] = nears[n]; }       // renderer.py:449-451
+    if (n == 0) {
+        FrameState s;
+        s.step = 0; s.n_alive = (int)N; s.n_step = 1;                    // N // N
+        s.m_padded = (int)(N + 128u - (N % 128u));
+        *state = s;
+        if (host_mailbox) { *host_mailbox = (int)N; __threadfence_system(); }
+    }
+}
+
+struct FrameWorkspace {
+    float *nears, *fars, *rays_t[2], *xyzs, *dirs, *deltas, *sigmas, *rgbs;
+    int* rays_alive[2];
+    FrameState* state;     // [2]
+    ScanWS* scan;
+    size_t bytes;
+};
+static FrameWorkspace carve_frame_workspace(void* base, uint32_t N) {
+    FrameWorkspace w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* p = base ? static_cast<char*>(base) + off : nullptr; off += (bytes + 255) & ~size_t(255); return p; };
+    const size_t Mmax = (size_t)N + 128;
+    w.state = static_cast<FrameState*>(take(2 * sizeof(FrameState)));
+    w.scan = static_cast<ScanWS*>(take(scan_ws_bytes(ceil_div<uint32_t>(N, kCompactThreads * kCompactItems))));
+    w.nears = static_cast<float*>(take(sizeof(float) * N));
+    w.fars = static_cast<float*>(take(sizeof(float) * N));
+    for (int i = 0; i < 2; i++) { w.rays_alive[i] = static_cast<int*>(take(sizeof(int) * N)); w.rays_t[i] = static_cast<float*>(take(sizeof(float) * N)); }
+    w.xyzs = static_cast<float*>(take(sizeof(float) * 3 * Mmax));
+    w.dirs = static_cast<float*>(take(sizeof(float) * 3 * Mmax));
+    w.deltas = static_cast<float*>(take(sizeof(float) * 2 * Mmax));
+    w.sigmas = static_cast<float*>(take(sizeof(float) * Mmax));
+    w.rgbs = static_cast<float*>(take(sizeof(float) * 3 * Mmax));
+    w.bytes = off;
+    return w;
+}
+}  // namespace ntx
+
+extern "C" size_t ntx_render_rays_workspace_bytes(uint32_t N) { return carve_frame_workspace(nullptr, N).bytes; }
+
+extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const float* aabb, float min_near, float bound, float dt_gamma,
+                               uint32_t max_steps, uint32_t perturb, uint32_t C, uint32_t H, const uint8_t* grid, const uint8_t* occupancy_mip,
+                               const void* embeddings_f16, const int* offsets, uint32_t L, float S, uint32_t base_resolution, int align_corners,
+                               const void* w_sigma_f16, const void* w_color_f16, float density_scale, float* weights_sum, float* depth, float* image,
+                               void* workspace, int* host_mailbox, unsigned long long* sample_counter, uint32_t* iterations_out, ntx_stream_t stream) {
+    NTX_REQUIRE(rays_o && rays_d && aabb && grid && weights_sum && depth && image, NTX_ERR_INVALID_ARGUMENT, "render_rays: null pointer");
+    NTX_REQUIRE(workspace, NTX_ERR_WORKSPACE, "render_rays: workspace of ntx_render_rays_workspace_bytes(N) bytes required");
+    NTX_REQUIRE(host_mailbox, NTX_ERR_INVALID_ARGUMENT, "render_rays: host_mailbox must point to max_steps + 1 ints of pinned (mapped) host memory");
+    NTX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, NTX_ERR_INVALID_ARGUMENT, "render_rays: workspace must be 256-byte aligned");
+    NTX_REQUIRE(C >= 1 && C <= 16 && H >= 1 && H <= 1024 && max_steps >= 1, NTX_ERR_INVALID_ARGUMENT, "render_rays: bad C/H/max_steps");
+    if (occupancy_mip && ((H & (H - 1)) != 0 || H < 16)) occupancy_mip = nullptr;
+    if (iterations_out) *iterations_out = 0;
+    if (N == 0) return NTX_OK;
+    cudaStream_t st = ST(stream);
+    const FrameWorkspace w = carve_frame_workspace(workspace, N);
+    // events that bound how far the launching thread runs ahead of the device (one set per process; the call is not re-entrant)
+    constexpr int kEvents = 4;
+    static cudaEvent_t ev[kEvents];
+    static bool ev_ready = false;
+    if (!ev_ready) {
+        for (int i = 0; i < kEvents; i++)
+            if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); set_error("render_rays: cannot create events"); return NTX_ERR_CUDA; }
+        ev_ready = true;
+    }
+    cudaMemsetAsync(w.state, 0, 2 * sizeof(FrameState), st);
+    cudaMemsetAsync(w.scan, 0, scan_ws_bytes(ceil_div<uint32_t>(N, kCompactThreads * kCompactItems)), st);
+    cudaMemsetAsync(weights_sum, 0, sizeof(float) * N, st);
+    cudaMemsetAsync(depth, 0, sizeof(float) * N, st);
+    cudaMemsetAsync(image, 0, sizeof(float) * 3 * N, st);
+    near_far_kernel<<<ceil_div<uint32_t>(N, 128), 128, 0, st>>>(rays_o, rays_d, aabb, N, min_near, w.nears, w.fars);
+    static bool smem_ready = false;
+    const size_t march_smem = (size_t)kMarchThreads * kMarchMaxStagedSteps * 8 * sizeof(float);
+    if (!smem_ready) {
+        cudaFuncSetAttribute(march_rays_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march_smem);
+        smem_ready = true;
+    }
+    uint32_t bound_rays = N, iterations = 0;
+    for (uint32_t i = 0; i < max_steps; i++) {
+        const int cur = i & 1, old = cur ^ 1;
+        FrameState* s_cur = w.state + cur;
+        if (i == 0) {
+            frame_init_kernel<<<ceil_div<uint32_t>(N, 256), 256, 0, st>>>(N, w.nears, w.rays_alive[0], w.rays_t[0], s_cur, host_mailbox);
+        } else {
+            compact_rays_kernel<<<ceil_div<uint32_t>(bound_rays, kCompactThreads * kCompactItems), kCompactThreads, 0, st>>>(
+                bound_rays, w.rays_alive[cur], w.rays_alive[old], w.rays_t[cur], w.rays_t[old], nullptr, w.scan, w.state + old, s_cur, N, max_steps, host_mailbox + i);
+        }
+        // padding rows (at most 128) are cleared by the first threads of the launch: at least one block
+        march_rays_staged_kernel<<<ceil_div<uint32_t>(max(bound_rays, 128u), kMarchThreads), kMarchThreads, march_smem, st>>>(
+            bound_rays, 1, w.rays_alive[cur], w.rays_t[cur], rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, w.nears, w.fars, w.xyzs, w.dirs, w.deltas, perturb, 0,
+            occupancy_mip, s_cur, sample_counter);
+        const uint32_t m_bound = min((uint32_t)N, bound_rays * 8u) + 128u;
+        const int rc = launch_ngp_field(w.xyzs, w.dirs, w.deltas, m_bound, &s_cur->m_padded, bound, embeddings_f16, offsets, L, S, base_resolution, align_corners,
+                                        w_sigma_f16, w_color_f16, density_scale, w.sigmas, w.rgbs, st);
+        if (rc != NTX_OK) return rc;
+        composite_rays_kernel<<<ceil_div<uint32_t>(bound_rays, 128), 128, 0, st>>>(bound_rays, 1, w.rays_alive[cur], w.rays_t[cur], w.sigmas, w.rgbs, w.deltas, weights_sum,
+                                                                                  depth, image, s_cur);
+        cudaEventRecord(ev[i % kEvents], st);
+        if (i >= 1) {
+            // iteration i-1 has certainly been planned once its event fires; iteration i is queued behind it, so the device
+            // never idles while this thread looks at the mailbox
+            if (cudaEventSynchronize(ev[(i - 1) % kEvents]) != cudaSuccess) return check_launch("render_rays");
+            const int alive = host_mailbox[i - 1];
+            if (alive <= 0) break;            // iteration i-1 found nothing alive; iteration i (already queued) is a no-op
+            iterations = i;                   // iterations 0 .. i-1 did work
+            bound_rays = (uint32_t)alive;     // n_alive never grows
+        }
+    }
+    if (iterations_out) *iterations_out = iterations;
+    return check_launch("render_rays");
 }

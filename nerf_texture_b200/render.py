@@ -75,19 +75,72 @@ class NGPField:
         return sig, rgb
 
 
+_frame_cache = {}
+
+
+def _frame_buffers(dev, N, max_steps):
+    """device workspace + pinned host mailbox of ntx_render_rays, cached per (device, stream, N)"""
+    key = (dev.index, L.stream(), N, max_steps)
+    buf = _frame_cache.get(key)
+    if buf is None:
+        ws = torch.empty(L.lib().ntx_render_rays_workspace_bytes(N) + 256, dtype=torch.uint8, device=dev)
+        off = (-ws.data_ptr()) % 256
+        mailbox = torch.zeros(max_steps + 1, dtype=torch.int32).pin_memory()
+        counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        buf = (ws, ws.data_ptr() + off, mailbox, counter)
+        _frame_cache.clear()          # one frame size at a time is the normal case; do not hoard workspaces
+        _frame_cache[key] = buf
+    return buf
+
+
+def _aabb_tensor(bound, dev, cache={}):
+    key = (float(bound), dev.index)
+    if key not in cache:
+        cache[key] = torch.tensor([-bound, -bound, -bound, bound, bound, bound], dtype=torch.float32, device=dev)
+    return cache[key]
+
+
 def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aabb=None, min_near=0.2, dt_gamma=0.0, max_steps=1024, bg_color=1.0,
-                perturb=0, count_samples=False, profile=None, use_mip=True):
+                perturb=0, count_samples=False, profile=None, use_mip=True, device_loop=True, mip=None):
     """Inference branch of NeRFRenderer.run_cuda (renderer.py:436-489).  rays_o/d [N,3] fp32 CUDA.
     Returns dict(image [N,3], depth [N], weights_sum [N], iterations, n_samples (if count_samples)).
-    profile: optional list; gets one (start_event, stop_event, live_sample_count_tensor) per field-kernel launch."""
+    device_loop=True (default): the whole loop is ONE libntx call whose iteration state stays on the device (ntx_render_rays);
+    device_loop=False: the reference's structure, one extension call per step and a blocking n_alive read per iteration
+    (bit-identical results; kept for profiling and as the parity reference of the device-driven loop).
+    profile: optional list (stepwise loop only); gets one (start_event, stop_event, live_sample_count_tensor) per field-kernel launch.
+    mip: optional pre-built occupancy mip (ntx_build_occupancy_mip) of density_bitfield."""
     dev = rays_o.device
     rays_o = rays_o.contiguous().view(-1, 3).float()
     rays_d = rays_d.contiguous().view(-1, 3).float()
     N = rays_o.shape[0]
     bound = field.bound
     if aabb is None:
-        aabb = torch.tensor([-bound, -bound, -bound, bound, bound, bound], dtype=torch.float32, device=dev)
+        aabb = _aabb_tensor(bound, dev)
     st = L.stream()
+    if use_mip and mip is None and grid_size >= 16 and (grid_size & (grid_size - 1)) == 0:
+        mip = torch.empty(L.lib().ntx_occupancy_mip_bytes(int(cascade), int(grid_size)), dtype=torch.uint8, device=dev)
+        L.call("ntx_build_occupancy_mip", L.ptr(density_bitfield), int(cascade), int(grid_size), L.ptr(mip), st)
+    if not use_mip:
+        mip = None
+    if device_loop and profile is None and N > 0:
+        import ctypes
+        ws, ws_ptr, mailbox, counter = _frame_buffers(dev, N, int(max_steps))
+        image_c = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        depth_c = torch.empty(N, dtype=torch.float32, device=dev)
+        wsum_c = torch.empty(N, dtype=torch.float32, device=dev)
+        if count_samples:
+            counter.zero_()
+        iters = ctypes.c_uint32(0)
+        L.call("ntx_render_rays", L.ptr(rays_o), L.ptr(rays_d), N, L.ptr(aabb), float(min_near), float(bound), float(dt_gamma), int(max_steps), int(perturb),
+               int(cascade), int(grid_size), L.ptr(density_bitfield), None if mip is None else L.ptr(mip), L.ptr(field.table), L.ptr(field.offsets),
+               field.num_levels, field.S, field.H, int(field.align_corners), L.ptr(field.w_sigma), L.ptr(field.w_color), float(field.density_scale),
+               L.ptr(wsum_c), L.ptr(depth_c), L.ptr(image_c), ws_ptr, mailbox.data_ptr(), counter.data_ptr() if count_samples else None,
+               ctypes.addressof(iters), st)
+        image = image_c + (1 - wsum_c).unsqueeze(-1) * bg_color
+        out = dict(image=image, depth=depth_c, weights_sum=wsum_c, iterations=int(iters.value))
+        if count_samples:
+            out["n_samples"] = int(counter.item())
+        return out
     nears = torch.empty(N, dtype=torch.float32, device=dev)
     fars = torch.empty(N, dtype=torch.float32, device=dev)
     L.call("ntx_near_far_from_aabb", L.ptr(rays_o), L.ptr(rays_d), L.ptr(aabb), N, float(min_near), L.ptr(nears), L.ptr(fars), st)
@@ -108,10 +161,6 @@ def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aab
     rgbs = torch.empty(Mmax, 3, dtype=torch.float32, device=dev)
     ws = L.workspace("compact", L.lib().ntx_compact_rays_workspace_bytes(N), dev)
     n_samples = torch.zeros(1, dtype=torch.int64, device=dev) if count_samples else None
-    mip = None
-    if use_mip and grid_size >= 16 and (grid_size & (grid_size - 1)) == 0:
-        mip = torch.empty(L.lib().ntx_occupancy_mip_bytes(int(cascade), int(grid_size)), dtype=torch.uint8, device=dev)
-        L.call("ntx_build_occupancy_mip", L.ptr(density_bitfield), int(cascade), int(grid_size), L.ptr(mip), st)
 
     n_alive, step, i = N, 0, 0
     while step < max_steps:

@@ -1,0 +1,67 @@
+"""GPU parity of the device-driven frame (ntx_render_rays: loop state on the device, no blocking n_alive read) against the
+stepwise loop that mirrors NeRFRenderer.run_cuda call by call (nerf/renderer.py:436-489).  Both run the same kernels on the
+same data in the same order, so everything must agree to the last bit — including the iteration count and the number of
+samples marched — for every way the loop can end (all rays dead, step budget exhausted) and for ragged ray counts."""
+import numpy as np
+import pytest
+import torch
+
+from _util import ntx
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _scene(hw, cascade, grid_size, bound, seed=0):
+    from nerf_texture_b200 import render, scene
+    field = render.NGPField.random(torch.device(DEV), bound=bound, seed=seed)
+    rays_o, rays_d = scene.pinhole_rays(hw[0], hw[1], DEV, radius=2.5 * bound)
+    bits = scene.ball_bitfield(cascade, grid_size, bound, DEV, radius=0.5 * bound)
+    return render, field, rays_o, rays_d, bits
+
+
+@pytest.mark.parametrize("hw,cascade,grid_size,bound,kw", [
+    ((64, 64), 1, 128, 1.0, dict()),
+    ((57, 41), 1, 128, 1.0, dict(perturb=7)),                       # ragged ray count, perturbed start
+    ((64, 64), 2, 64, 2.0, dict(dt_gamma=1.0 / 128)),               # two cascades, growing steps
+    ((64, 64), 1, 128, 1.0, dict(max_steps=24)),                    # the step budget ends the loop, rays still alive
+    ((64, 64), 1, 128, 1.0, dict(use_mip=False)),
+    ((3, 5), 1, 128, 1.0, dict()),                                  # fewer rays than one block
+], ids=["plain", "ragged_perturb", "cascades_dtgamma", "step_budget", "no_mip", "tiny"])
+def test_device_driven_frame_equals_stepwise_loop(hw, cascade, grid_size, bound, kw):
+    ntx()
+    render, field, rays_o, rays_d, bits = _scene(hw, cascade, grid_size, bound)
+    a = render.render_rays(field, rays_o, rays_d, bits, cascade, grid_size, count_samples=True, device_loop=False, **kw)
+    b = render.render_rays(field, rays_o, rays_d, bits, cascade, grid_size, count_samples=True, device_loop=True, **kw)
+    assert a["iterations"] == b["iterations"] and a["iterations"] > 0
+    assert a["n_samples"] == b["n_samples"] and a["n_samples"] > 0
+    for k in ("image", "depth", "weights_sum"):
+        np.testing.assert_array_equal(a[k].cpu().numpy(), b[k].cpu().numpy(), err_msg=k)
+
+
+def test_device_driven_frame_is_repeatable_and_reuses_its_workspace():
+    ntx()
+    render, field, rays_o, rays_d, bits = _scene((96, 96), 1, 128, 1.0, seed=3)
+    outs = [render.render_rays(field, rays_o, rays_d, bits, 1, 128, count_samples=True) for _ in range(5)]
+    for o in outs[1:]:
+        assert o["iterations"] == outs[0]["iterations"] and o["n_samples"] == outs[0]["n_samples"]
+        assert torch.equal(o["image"], outs[0]["image"]) and torch.equal(o["depth"], outs[0]["depth"])
+    # a frame with no occupied voxel at all: nothing is marched, the image is the background
+    empty = torch.zeros_like(bits)
+    o = render.render_rays(field, rays_o, rays_d, empty, 1, 128, count_samples=True)
+    assert o["n_samples"] == 0 and o["iterations"] <= 1
+    assert torch.equal(o["image"], torch.ones_like(o["image"])) and float(o["weights_sum"].abs().max()) == 0.0
+
+
+def test_render_rays_rejects_missing_workspace_and_mailbox():
+    L = ntx()
+    import ctypes
+    it = ctypes.c_uint32(0)
+    d = torch.zeros(16, device=DEV)
+    args = [d.data_ptr(), d.data_ptr(), 1, d.data_ptr(), 0.2, 1.0, 0.0, 8, 0, 1, 128, d.data_ptr(), None, d.data_ptr(), d.data_ptr(), 16, 0.5, 16, 1, d.data_ptr(),
+            d.data_ptr(), 1.0, d.data_ptr(), d.data_ptr(), d.data_ptr()]
+    with pytest.raises(RuntimeError, match="workspace"):
+        L.call("ntx_render_rays", *args, None, None, None, ctypes.addressof(it), L.stream())
+    ws = torch.zeros(1 << 16, dtype=torch.uint8, device=DEV)
+    with pytest.raises(RuntimeError, match="mailbox"):
+        L.call("ntx_render_rays", *args, ws.data_ptr() + (-ws.data_ptr()) % 256, None, None, ctypes.addressof(it), L.stream())
