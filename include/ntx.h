@@ -173,7 +173,7 @@ int ntx_ngp_field_forward(const float* xyz, const float* dirs, const float* delt
  *   workspace: ntx_render_rays_workspace_bytes(N) bytes of device memory, 256-byte aligned
  *   host_mailbox: max_steps + 1 ints of pinned, device-mapped host memory (cudaHostAlloc / torch pin_memory)
  *   sample_counter: nullable device counter, incremented by the number of samples marched (statistics)
- *   iterations_out: nullable host pointer, number of loop iterations that had rays alive
+ *   stats_out: nullable host pointer to 2 uint32: [0] loop iterations that had rays alive, [1] kernels launched by this call
  * Not re-entrant (uses one set of events per process). */
 size_t ntx_render_rays_workspace_bytes(uint32_t N);
 int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const float* aabb, float min_near, float bound,
@@ -181,7 +181,7 @@ int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const 
                     const uint8_t* occupancy_mip, const void* embeddings_f16, const int* offsets, uint32_t L, float S,
                     uint32_t base_resolution, int align_corners, const void* w_sigma_f16, const void* w_color_f16,
                     float density_scale, float* weights_sum, float* depth, float* image, void* workspace,
-                    int* host_mailbox, unsigned long long* sample_counter, uint32_t* iterations_out, ntx_stream_t stream);
+                    int* host_mailbox, unsigned long long* sample_counter, uint32_t* stats_out, ntx_stream_t stream);
 
 #ifdef __cplusplus
 }

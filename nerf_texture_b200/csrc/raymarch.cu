@@ -1070,14 +1070,14 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
                                uint32_t max_steps, uint32_t perturb, uint32_t C, uint32_t H, const uint8_t* grid, const uint8_t* occupancy_mip,
                                const void* embeddings_f16, const int* offsets, uint32_t L, float S, uint32_t base_resolution, int align_corners,
                                const void* w_sigma_f16, const void* w_color_f16, float density_scale, float* weights_sum, float* depth, float* image,
-                               void* workspace, int* host_mailbox, unsigned long long* sample_counter, uint32_t* iterations_out, ntx_stream_t stream) {
+                               void* workspace, int* host_mailbox, unsigned long long* sample_counter, uint32_t* stats_out, ntx_stream_t stream) {
     NTX_REQUIRE(rays_o && rays_d && aabb && grid && weights_sum && depth && image, NTX_ERR_INVALID_ARGUMENT, "render_rays: null pointer");
     NTX_REQUIRE(workspace, NTX_ERR_WORKSPACE, "render_rays: workspace of ntx_render_rays_workspace_bytes(N) bytes required");
     NTX_REQUIRE(host_mailbox, NTX_ERR_INVALID_ARGUMENT, "render_rays: host_mailbox must point to max_steps + 1 ints of pinned (mapped) host memory");
     NTX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, NTX_ERR_INVALID_ARGUMENT, "render_rays: workspace must be 256-byte aligned");
     NTX_REQUIRE(C >= 1 && C <= 16 && H >= 1 && H <= 1024 && max_steps >= 1, NTX_ERR_INVALID_ARGUMENT, "render_rays: bad C/H/max_steps");
     if (occupancy_mip && ((H & (H - 1)) != 0 || H < 16)) occupancy_mip = nullptr;
-    if (iterations_out) *iterations_out = 0;
+    if (stats_out) stats_out[0] = stats_out[1] = 0;
     if (N == 0) return NTX_OK;
     cudaStream_t st = ST(stream);
     const FrameWorkspace w = carve_frame_workspace(workspace, N);
@@ -1102,7 +1102,7 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
         cudaFuncSetAttribute(march_rays_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march_smem);
         smem_ready = true;
     }
-    uint32_t bound_rays = N, iterations = 0;
+    uint32_t bound_rays = N, iterations = 0, kernels = 1;   // near_far
     for (uint32_t i = 0; i < max_steps; i++) {
         const int cur = i & 1, old = cur ^ 1;
         FrameState* s_cur = w.state + cur;
@@ -1122,6 +1122,7 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
         if (rc != NTX_OK) return rc;
         composite_rays_kernel<<<ceil_div<uint32_t>(bound_rays, 128), 128, 0, st>>>(bound_rays, 1, w.rays_alive[cur], w.rays_t[cur], w.sigmas, w.rgbs, w.deltas, weights_sum,
                                                                                   depth, image, s_cur);
+        kernels += 4;                                       // init | compact, march, field, composite
         cudaEventRecord(ev[i % kEvents], st);
         if (i >= 1) {
             // iteration i-1 has certainly been planned once its event fires; iteration i is queued behind it, so the device
@@ -1133,6 +1134,6 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
             bound_rays = (uint32_t)alive;     // n_alive never grows
         }
     }
-    if (iterations_out) *iterations_out = iterations;
+    if (stats_out) { stats_out[0] = iterations; stats_out[1] = kernels; }
     return check_launch("render_rays");
 }

@@ -130,14 +130,15 @@ def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aab
         wsum_c = torch.empty(N, dtype=torch.float32, device=dev)
         if count_samples:
             counter.zero_()
-        iters = ctypes.c_uint32(0)
+        stats = (ctypes.c_uint32 * 2)()
         L.call("ntx_render_rays", L.ptr(rays_o), L.ptr(rays_d), N, L.ptr(aabb), float(min_near), float(bound), float(dt_gamma), int(max_steps), int(perturb),
                int(cascade), int(grid_size), L.ptr(density_bitfield), None if mip is None else L.ptr(mip), L.ptr(field.table), L.ptr(field.offsets),
                field.num_levels, field.S, field.H, int(field.align_corners), L.ptr(field.w_sigma), L.ptr(field.w_color), float(field.density_scale),
                L.ptr(wsum_c), L.ptr(depth_c), L.ptr(image_c), ws_ptr, mailbox.data_ptr(), counter.data_ptr() if count_samples else None,
-               ctypes.addressof(iters), st)
+               ctypes.addressof(stats), st)
+        L.launches += int(stats[1]) - 1          # L.call counted the call as one launch
         image = image_c + (1 - wsum_c).unsqueeze(-1) * bg_color
-        out = dict(image=image, depth=depth_c, weights_sum=wsum_c, iterations=int(iters.value))
+        out = dict(image=image, depth=depth_c, weights_sum=wsum_c, iterations=int(stats[0]))
         if count_samples:
             out["n_samples"] = int(counter.item())
         return out

@@ -56,7 +56,7 @@ def test_device_driven_frame_is_repeatable_and_reuses_its_workspace():
 def test_render_rays_rejects_missing_workspace_and_mailbox():
     L = ntx()
     import ctypes
-    it = ctypes.c_uint32(0)
+    it = (ctypes.c_uint32 * 2)()
     d = torch.zeros(16, device=DEV)
     args = [d.data_ptr(), d.data_ptr(), 1, d.data_ptr(), 0.2, 1.0, 0.0, 8, 0, 1, 128, d.data_ptr(), None, d.data_ptr(), d.data_ptr(), 16, 0.5, 16, 1, d.data_ptr(),
             d.data_ptr(), 1.0, d.data_ptr(), d.data_ptr(), d.data_ptr()]
