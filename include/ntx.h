@@ -168,16 +168,23 @@ int ntx_ngp_field_forward(const float* xyz, const float* dirs, const float* delt
  * the device (the kernels read n_alive / n_step from it), grids are sized from a bound that lags two iterations behind
  * through a pinned host mailbox, and the launching thread never lets the stream run dry.  Results are bit-identical to
  * calling the individual entry points in the reference's order.
+ *   sample_budget, max_n_step: samples per iteration n_step = clamp(sample_budget // n_alive, 1, max_n_step).  (0, 0) = (N, 8) is
+ *     the reference's schedule.  The image does not depend on the schedule (a ray's samples are composited in the same order and
+ *     stop at the same sample; only how many iterations that takes, and how many samples past an opaque ray's stop are evaluated
+ *     and discarded, changes), so a B200 with memory to spare can run e.g. (4N, 32) and cut the number of iterations.
+ *     Exceptions: perturb != 0 (the reference jitters t once per march_rays call, so the schedule is part of the random
+ *     realisation) and rays that need more than max_steps samples (the step budget is checked once per iteration).
  *   rays_o, rays_d [N,3] f32; aabb [6] f32 (device); grid = density bit-field; occupancy_mip nullable (ntx_build_occupancy_mip)
  *   weights_sum [N], depth [N], image [N,3] f32: overwritten (image WITHOUT the background term, like composite_rays)
- *   workspace: ntx_render_rays_workspace_bytes(N) bytes of device memory, 256-byte aligned
+ *   workspace: ntx_render_rays_workspace_bytes(N, sample_budget) bytes of device memory, 256-byte aligned
  *   host_mailbox: max_steps + 1 ints of pinned, device-mapped host memory (cudaHostAlloc / torch pin_memory)
  *   sample_counter: nullable device counter, incremented by the number of samples marched (statistics)
  *   stats_out: nullable host pointer to 2 uint32: [0] loop iterations that had rays alive, [1] kernels launched by this call
  * Not re-entrant (uses one set of events per process). */
-size_t ntx_render_rays_workspace_bytes(uint32_t N);
+size_t ntx_render_rays_workspace_bytes(uint32_t N, uint32_t sample_budget);
 int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const float* aabb, float min_near, float bound,
-                    float dt_gamma, uint32_t max_steps, uint32_t perturb, uint32_t C, uint32_t H, const uint8_t* grid,
+                    float dt_gamma, uint32_t max_steps, uint32_t perturb, uint32_t sample_budget, uint32_t max_n_step,
+                    uint32_t C, uint32_t H, const uint8_t* grid,
                     const uint8_t* occupancy_mip, const void* embeddings_f16, const int* offsets, uint32_t L, float S,
                     uint32_t base_resolution, int align_corners, const void* w_sigma_f16, const void* w_color_f16,
                     float density_scale, float* weights_sum, float* depth, float* image, void* workspace,

@@ -684,11 +684,8 @@ __global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
     const uint8_t* __restrict__ grid, const float* __restrict__ nears, const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs,
     float* __restrict__ deltas, const uint32_t perturb, uint32_t M_padded, const uint8_t* __restrict__ coarse, const FrameState* __restrict__ state,
     unsigned long long* __restrict__ sample_counter) {
-    extern __shared__ __align__(16) float stage[];          // [128*n_step*3] xyz | [128*n_step*3] dir | [128*n_step*2] delta
+    extern __shared__ __align__(16) float stage[];          // [128*nc*3] xyz | [128*nc*3] dir | [128*nc*2] delta, nc = min(n_step, 8)
     if (state) { n_alive = (uint32_t)state->n_alive; n_step = (uint32_t)state->n_step; M_padded = (uint32_t)state->m_padded; }
-    float* sx = stage;
-    float* sd = stage + kMarchThreads * n_step * 3;
-    float* sl = sd + kMarchThreads * n_step * 3;
     const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
     {   // padding rows beyond n_alive*n_step (align-to-128 tail, raymarching.py:386-387)
         const uint32_t row = n_alive * n_step + n;
@@ -700,15 +697,17 @@ __global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
     }
     const uint32_t first = blockIdx.x * kMarchThreads;
     if (first >= n_alive) return;                            // block only had padding rows to clear
-    if (n < n_alive) {
+    const bool mine = n < n_alive;
+    const uint32_t rays_here = min((uint32_t)kMarchThreads, n_alive - first);
+    Ray r;
+    float t = 0.f, far = 0.f, last_t = 0.f;
+    const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H, grid);
+    bool exhausted = !mine;                                  // nothing (more) to emit on this ray
+    if (mine) {
         const int index = rays_alive[n];
-        float t = rays_t[n];
-        const Ray r = load_ray(rays_o + (size_t)index * 3, rays_d + (size_t)index * 3);
-        const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H, grid);
-        float* px = sx + threadIdx.x * n_step * 3;
-        float* pd = sd + threadIdx.x * n_step * 3;
-        float* pl = sl + threadIdx.x * n_step * 2;
-        float far = fars[index];
+        t = rays_t[n];
+        r = load_ray(rays_o + (size_t)index * 3, rays_d + (size_t)index * 3);
+        far = fars[index];
         if (perturb) {
             Pcg32 rng; rng.seed((uint64_t)perturb);   // raymarching.cu:1011
             rng.advance(n);
@@ -720,78 +719,108 @@ __global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
             float b_lo, b_hi;
             if (clip_to_occupied(r, p, coarse, b_lo, b_hi)) far = fminf(far, b_hi); else far = t;
         }
-        float last_t = t, x, y, z, dt;
+        last_t = t;
+    }
+    uint32_t emitted = 0, empties = 0;
+    // The ray's n_step output rows are produced in chunks of at most 8 (the reference never asks for more than 8; wider
+    // schedules of ntx_render_rays do): a chunk is staged in shared memory and written out before the next one starts.
+    for (uint32_t c0 = 0; c0 < n_step; c0 += kMarchMaxStagedSteps) {
+        const uint32_t nc = min(kMarchMaxStagedSteps, n_step - c0);
+        float* sx = stage;
+        float* sd = stage + kMarchThreads * nc * 3;
+        float* sl = sd + kMarchThreads * nc * 3;
+        float* px = sx + threadIdx.x * nc * 3;
+        float* pd = sd + threadIdx.x * nc * 3;
+        float* pl = sl + threadIdx.x * nc * 2;
         uint32_t step = 0;
-        {
-            // Speculation: inside the object every probe is occupied, so the next n_step sample positions are t, t+dt, ...
-            // (the same float additions the sequential marcher performs).  Issue all their occupancy loads at once instead
-            // of one dependent load per step, then accept the longest all-occupied prefix; the first empty voxel falls back
-            // to the sequential loop below at exactly the state the reference would be in.
-            float tq[kMarchMaxStagedSteps];
-            uint32_t bitidx[kMarchMaxStagedSteps], byte[kMarchMaxStagedSteps];
-            float tcur = t;
-            uint32_t nspec = 0;
+        if (mine) {
+            float x, y, z, dt;
+            if (!exhausted) {
+                // Speculation: inside the object every probe is occupied, so the next nc sample positions are t, t+dt, ...
+                // (the same float additions the sequential marcher performs).  Issue all their occupancy loads at once instead
+                // of one dependent load per step, then accept the longest all-occupied prefix; the first empty voxel falls back
+                // to the sequential loop below at exactly the state the reference would be in.
+                float tq[kMarchMaxStagedSteps];
+                uint32_t bitidx[kMarchMaxStagedSteps], byte[kMarchMaxStagedSteps];
+                float tcur = t;
+                uint32_t nspec = 0;
 #pragma unroll
-            for (uint32_t s = 0; s < kMarchMaxStagedSteps; s++) {
-                tq[s] = tcur; bitidx[s] = 0; byte[s] = 0;
-                if (s < n_step && tcur < far) {
-                    const uint32_t index = locate(r, p, tcur, x, y, z, dt);
-                    bitidx[s] = index & 7u;
-                    byte[s] = p.grid[index >> 3];
-                    tcur += dt;
-                    nspec = s + 1;
+                for (uint32_t s = 0; s < kMarchMaxStagedSteps; s++) {
+                    tq[s] = tcur; bitidx[s] = 0; byte[s] = 0;
+                    if (s < nc && tcur < far) {
+                        const uint32_t index = locate(r, p, tcur, x, y, z, dt);
+                        bitidx[s] = index & 7u;
+                        byte[s] = p.grid[index >> 3];
+                        tcur += dt;
+                        nspec = s + 1;
+                    }
                 }
-            }
 #pragma unroll
-            for (uint32_t s = 0; s < kMarchMaxStagedSteps; s++) {
-                if (s < nspec && step == s) {                     // step == s: all earlier speculated probes were occupied
-                    if (byte[s] & (1u << bitidx[s])) {
-                        locate(r, p, tq[s], x, y, z, dt);
+                for (uint32_t s = 0; s < kMarchMaxStagedSteps; s++) {
+                    if (s < nspec && step == s) {                     // step == s: all earlier speculated probes were occupied
+                        if (byte[s] & (1u << bitidx[s])) {
+                            locate(r, p, tq[s], x, y, z, dt);
+                            px[0] = x; px[1] = y; px[2] = z;
+                            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+                            t = tq[s] + dt;
+                            pl[0] = dt; pl[1] = t - last_t;
+                            last_t = t;
+                            px += 3; pd += 3; pl += 2; step++;
+                        }
+                    }
+                }
+                while (t < far && step < nc) {
+                    if (probe(r, p, t, x, y, z, dt)) {
                         px[0] = x; px[1] = y; px[2] = z;
                         pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
-                        t = tq[s] + dt;
+                        t += dt;
                         pl[0] = dt; pl[1] = t - last_t;
                         last_t = t;
                         px += 3; pd += 3; pl += 2; step++;
+                    } else if (coarse && ((empties++ & 3u) == 0u)) {
+                        // in empty space: if nothing occupied can be reached any more, this ray emits no further sample and is dead
+                        // after composite_rays whatever t it stops at — skip the voxel-by-voxel walk to `far`
+                        if (!maybe_occupied_ahead(r, p, coarse, t, far)) { far = t; break; }
                     }
                 }
+                if (step < nc) exhausted = true;                 // ran out of ray: every later slot is a sentinel
+                emitted += step;
+            }
+            for (; step < nc; step++) {                          // unused slots: zero (delta == 0 is composite_rays' stop sentinel)
+                px[0] = 0; px[1] = 0; px[2] = 0; pd[0] = 0; pd[1] = 0; pd[2] = 0; pl[0] = 0; pl[1] = 0;
+                px += 3; pd += 3; pl += 2;
             }
         }
-        uint32_t empties = 0;
-        while (t < far && step < n_step) {
-            if (probe(r, p, t, x, y, z, dt)) {
-                px[0] = x; px[1] = y; px[2] = z;
-                pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
-                t += dt;
-                pl[0] = dt; pl[1] = t - last_t;
-                last_t = t;
-                px += 3; pd += 3; pl += 2; step++;
-            } else if (coarse && ((empties++ & 3u) == 0u)) {
-                // in empty space: if nothing occupied can be reached any more, this ray emits no further sample and is dead
-                // after composite_rays whatever t it stops at — skip the voxel-by-voxel walk to `far`
-                if (!maybe_occupied_ahead(r, p, coarse, t, far)) break;
+        __syncthreads();
+        if (nc == n_step) {
+            // the block's rows form one contiguous segment of each output
+            const size_t row0 = (size_t)first * n_step;
+            block_copy_out(xyzs + row0 * 3, sx, rays_here * n_step * 3);
+            block_copy_out(dirs + row0 * 3, sd, rays_here * n_step * 3);
+            block_copy_out(deltas + row0 * 2, sl, rays_here * n_step * 2);
+        } else {
+            // one segment of nc rows per ray, n_step rows apart
+            for (uint32_t i = threadIdx.x; i < rays_here * nc * 3; i += kMarchThreads) {
+                const uint32_t ray = i / (nc * 3), o = i - ray * (nc * 3);
+                const size_t dst = ((size_t)(first + ray) * n_step + c0) * 3 + o;
+                xyzs[dst] = sx[i]; dirs[dst] = sd[i];
+            }
+            for (uint32_t i = threadIdx.x; i < rays_here * nc * 2; i += kMarchThreads) {
+                const uint32_t ray = i / (nc * 2), o = i - ray * (nc * 2);
+                deltas[((size_t)(first + ray) * n_step + c0) * 2 + o] = sl[i];
             }
         }
-        if (sample_counter) {                                // bench / statistics only: samples emitted in this launch
-            if (__activemask() == 0xffffffffu) {             // full warp: one atomic per warp
-                uint32_t cnt = step;
-                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-                if ((threadIdx.x & 31) == 0) atomicAdd(sample_counter, (unsigned long long)cnt);
-            } else {
-                atomicAdd(sample_counter, (unsigned long long)step);
-            }
-        }
-        for (; step < n_step; step++) {                      // unused slots: zero (delta == 0 is composite_rays' stop sentinel)
-            px[0] = 0; px[1] = 0; px[2] = 0; pd[0] = 0; pd[1] = 0; pd[2] = 0; pl[0] = 0; pl[1] = 0;
-            px += 3; pd += 3; pl += 2;
+        __syncthreads();
+    }
+    if (sample_counter && mine) {                                // bench / statistics only: samples emitted in this launch
+        if (__activemask() == 0xffffffffu) {                     // full warp: one atomic per warp
+            uint32_t cnt = emitted;
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(sample_counter, (unsigned long long)cnt);
+        } else {
+            atomicAdd(sample_counter, (unsigned long long)emitted);
         }
     }
-    __syncthreads();
-    const uint32_t rays_here = min((uint32_t)kMarchThreads, n_alive - first);
-    const size_t row0 = (size_t)first * n_step;
-    block_copy_out(xyzs + row0 * 3, sx, rays_here * n_step * 3);
-    block_copy_out(dirs + row0 * 3, sd, rays_here * n_step * 3);
-    block_copy_out(deltas + row0 * 2, sl, rays_here * n_step * 2);
 }
 
 // raymarching.cu:1021-1104
@@ -835,7 +864,8 @@ constexpr int kCompactItems = 4;
 __global__ void __launch_bounds__(kCompactThreads) compact_rays_kernel(uint32_t n_alive, int* __restrict__ rays_alive, const int* __restrict__ rays_alive_old,
                                                                        float* __restrict__ rays_t, const float* __restrict__ rays_t_old, int* __restrict__ alive_counter,
                                                                        ScanWS* ws, const FrameState* __restrict__ state_in, FrameState* __restrict__ state_out,
-                                                                       const uint32_t n_rays, const uint32_t max_steps, volatile int* host_mailbox) {
+                                                                       const uint32_t budget, const uint32_t max_n_step, const uint32_t max_steps,
+                                                                       volatile int* host_mailbox) {
     if (state_in) n_alive = (uint32_t)state_in->n_alive;
     __shared__ uint32_t s_ticket;
     __shared__ uint32_t s_warp[33];
@@ -865,7 +895,7 @@ __global__ void __launch_bounds__(kCompactThreads) compact_rays_kernel(uint32_t 
             FrameState s;
             s.step = state_in->step + state_in->n_step;                       // step += n_step   (renderer.py:475)
             s.n_alive = ((uint32_t)s.step < max_steps) ? (int)total : 0;       // while step < max_steps
-            s.n_step = s.n_alive ? (int)max(min(n_rays / (uint32_t)s.n_alive, 8u), 1u) : 0;   // renderer.py:464
+            s.n_step = s.n_alive ? (int)max(min(budget / (uint32_t)s.n_alive, max_n_step), 1u) : 0;   // renderer.py:464 with (N, 8)
             const uint32_t m = (uint32_t)s.n_alive * (uint32_t)s.n_step;
             s.m_padded = s.n_alive ? (int)(m + 128u - (m % 128u)) : 0;         // raymarching.py:386-387 (align = 128)
             *state_out = s;
@@ -972,8 +1002,8 @@ extern "C" int ntx_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays
     uint32_t threads = n_alive;
     if (zero_fill) threads = max(threads, M_padded - n_alive * n_step);
     if (threads == 0) return NTX_OK;
-    if (zero_fill && n_step >= 1 && n_step <= kMarchMaxStagedSteps && ((reinterpret_cast<uintptr_t>(xyzs) | reinterpret_cast<uintptr_t>(dirs) | reinterpret_cast<uintptr_t>(deltas)) & 15) == 0) {
-        const size_t smem = (size_t)kMarchThreads * n_step * 8 * sizeof(float);
+    if (zero_fill && n_step >= 1 && ((reinterpret_cast<uintptr_t>(xyzs) | reinterpret_cast<uintptr_t>(dirs) | reinterpret_cast<uintptr_t>(deltas)) & 15) == 0) {
+        const size_t smem = (size_t)kMarchThreads * min(n_step, kMarchMaxStagedSteps) * 8 * sizeof(float);
         march_rays_staged_kernel<<<ceil_div<uint32_t>(threads, kMarchThreads), kMarchThreads, smem, ST(stream)>>>(
             n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs, dirs, deltas, perturb, M_padded,
             occupancy_mip, nullptr, nullptr);
@@ -1018,20 +1048,22 @@ extern "C" int ntx_compact_rays(uint32_t n_alive, int* rays_alive, const int* ra
     compact_rays_kernel<<<ceil_div<uint32_t>(n_alive, kCompactThreads * kCompactItems), kCompactThreads, 0, ST(stream)>>>(n_alive, rays_alive, rays_alive_old, rays_t,
                                                                                                                          rays_t_old, alive_counter,
                                                                                                                          static_cast<ScanWS*>(workspace), nullptr, nullptr,
-                                                                                                                         0, 0, nullptr);
+                                                                                                                         0, 0, 0, nullptr);
     return check_launch("compact_rays");
 }
 
 // ---------------------------------------------------------------------------------------------------- device-driven frame
 namespace ntx {
-__global__ void __launch_bounds__(256) frame_init_kernel(const uint32_t N, const float* __restrict__ nears, int* __restrict__ rays_alive, float* __restrict__ rays_t,
-                                                         FrameState* __restrict__ state, volatile int* host_mailbox) {
+__global__ void __launch_bounds__(256) frame_init_kernel(const uint32_t N, const uint32_t budget, const uint32_t max_n_step, const float* __restrict__ nears,
+                                                         int* __restrict__ rays_alive, float* __restrict__ rays_t, FrameState* __restrict__ state,
+                                                         volatile int* host_mailbox) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n < N) { rays_alive[n] = (int)n; rays_t[n] = nears[n]; }       // renderer.py:449-451
     if (n == 0) {
         FrameState s;
-        s.step = 0; s.n_alive = (int)N; s.n_step = 1;                    // N // N
-        s.m_padded = (int)(N + 128u - (N % 128u));
+        s.step = 0; s.n_alive = (int)N; s.n_step = (int)max(min(budget / N, max_n_step), 1u);   // N // N = 1 for the reference schedule
+        const uint32_t m = N * (uint32_t)s.n_step;
+        s.m_padded = (int)(m + 128u - (m % 128u));
         *state = s;
         if (host_mailbox) { *host_mailbox = (int)N; __threadfence_system(); }
     }
@@ -1044,11 +1076,11 @@ struct FrameWorkspace {
     ScanWS* scan;
     size_t bytes;
 };
-static FrameWorkspace carve_frame_workspace(void* base, uint32_t N) {
+static FrameWorkspace carve_frame_workspace(void* base, uint32_t N, uint32_t budget) {
     FrameWorkspace w;
     size_t off = 0;
     auto take = [&](size_t bytes) { void* p = base ? static_cast<char*>(base) + off : nullptr; off += (bytes + 255) & ~size_t(255); return p; };
-    const size_t Mmax = (size_t)N + 128;
+    const size_t Mmax = (size_t)max(N, budget) + 128;        // n_alive * n_step <= max(budget, n_alive)
     w.state = static_cast<FrameState*>(take(2 * sizeof(FrameState)));
     w.scan = static_cast<ScanWS*>(take(scan_ws_bytes(ceil_div<uint32_t>(N, kCompactThreads * kCompactItems))));
     w.nears = static_cast<float*>(take(sizeof(float) * N));
@@ -1064,10 +1096,13 @@ static FrameWorkspace carve_frame_workspace(void* base, uint32_t N) {
 }
 }  // namespace ntx
 
-extern "C" size_t ntx_render_rays_workspace_bytes(uint32_t N) { return carve_frame_workspace(nullptr, N).bytes; }
+extern "C" size_t ntx_render_rays_workspace_bytes(uint32_t N, uint32_t sample_budget) {
+    return carve_frame_workspace(nullptr, N, sample_budget ? sample_budget : N).bytes;
+}
 
 extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const float* aabb, float min_near, float bound, float dt_gamma,
-                               uint32_t max_steps, uint32_t perturb, uint32_t C, uint32_t H, const uint8_t* grid, const uint8_t* occupancy_mip,
+                               uint32_t max_steps, uint32_t perturb, uint32_t sample_budget, uint32_t max_n_step, uint32_t C, uint32_t H, const uint8_t* grid,
+                               const uint8_t* occupancy_mip,
                                const void* embeddings_f16, const int* offsets, uint32_t L, float S, uint32_t base_resolution, int align_corners,
                                const void* w_sigma_f16, const void* w_color_f16, float density_scale, float* weights_sum, float* depth, float* image,
                                void* workspace, int* host_mailbox, unsigned long long* sample_counter, uint32_t* stats_out, ntx_stream_t stream) {
@@ -1079,8 +1114,11 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
     if (occupancy_mip && ((H & (H - 1)) != 0 || H < 16)) occupancy_mip = nullptr;
     if (stats_out) stats_out[0] = stats_out[1] = 0;
     if (N == 0) return NTX_OK;
+    if (sample_budget == 0) sample_budget = N;     // the reference's schedule: n_step = clamp(N // n_alive, 1, 8)   (renderer.py:464)
+    if (max_n_step == 0) max_n_step = 8;
+    NTX_REQUIRE(max_n_step <= 1024 && (uint64_t)max(N, sample_budget) + 128 < (1ull << 31), NTX_ERR_INVALID_ARGUMENT, "render_rays: bad sample_budget / max_n_step");
     cudaStream_t st = ST(stream);
-    const FrameWorkspace w = carve_frame_workspace(workspace, N);
+    const FrameWorkspace w = carve_frame_workspace(workspace, N, sample_budget);
     // events that bound how far the launching thread runs ahead of the device (one set per process; the call is not re-entrant)
     constexpr int kEvents = 4;
     static cudaEvent_t ev[kEvents];
@@ -1107,16 +1145,17 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
         const int cur = i & 1, old = cur ^ 1;
         FrameState* s_cur = w.state + cur;
         if (i == 0) {
-            frame_init_kernel<<<ceil_div<uint32_t>(N, 256), 256, 0, st>>>(N, w.nears, w.rays_alive[0], w.rays_t[0], s_cur, host_mailbox);
+            frame_init_kernel<<<ceil_div<uint32_t>(N, 256), 256, 0, st>>>(N, sample_budget, max_n_step, w.nears, w.rays_alive[0], w.rays_t[0], s_cur, host_mailbox);
         } else {
             compact_rays_kernel<<<ceil_div<uint32_t>(bound_rays, kCompactThreads * kCompactItems), kCompactThreads, 0, st>>>(
-                bound_rays, w.rays_alive[cur], w.rays_alive[old], w.rays_t[cur], w.rays_t[old], nullptr, w.scan, w.state + old, s_cur, N, max_steps, host_mailbox + i);
+                bound_rays, w.rays_alive[cur], w.rays_alive[old], w.rays_t[cur], w.rays_t[old], nullptr, w.scan, w.state + old, s_cur, sample_budget, max_n_step, max_steps,
+                host_mailbox + i);
         }
         // padding rows (at most 128) are cleared by the first threads of the launch: at least one block
         march_rays_staged_kernel<<<ceil_div<uint32_t>(max(bound_rays, 128u), kMarchThreads), kMarchThreads, march_smem, st>>>(
             bound_rays, 1, w.rays_alive[cur], w.rays_t[cur], rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, w.nears, w.fars, w.xyzs, w.dirs, w.deltas, perturb, 0,
             occupancy_mip, s_cur, sample_counter);
-        const uint32_t m_bound = min((uint32_t)N, bound_rays * 8u) + 128u;
+        const uint32_t m_bound = (uint32_t)min((uint64_t)max(N, sample_budget), (uint64_t)bound_rays * max_n_step) + 128u;
         const int rc = launch_ngp_field(w.xyzs, w.dirs, w.deltas, m_bound, &s_cur->m_padded, bound, embeddings_f16, offsets, L, S, base_resolution, align_corners,
                                         w_sigma_f16, w_color_f16, density_scale, w.sigmas, w.rgbs, st);
         if (rc != NTX_OK) return rc;

@@ -78,12 +78,27 @@ class NGPField:
 _frame_cache = {}
 
 
-def _frame_buffers(dev, N, max_steps):
-    """device workspace + pinned host mailbox of ntx_render_rays, cached per (device, stream, N)"""
-    key = (dev.index, L.stream(), N, max_steps)
+SCHEDULES = {
+    # name: (sample budget per iteration as a multiple of N, max samples per ray per iteration)
+    "reference": (1, 8),     # n_step = clamp(N // n_alive, 1, 8)   (renderer.py:464)
+    "wide": (4, 32),         # same image, ~3x fewer loop iterations; evaluates (and discards) more samples behind opaque hits
+}
+
+
+def auto_schedule(N):
+    """Keep about 2^20 sample rows per iteration whatever the number of rays: a rank that renders 1/8 of a frame marches 8x
+    more samples per ray and iteration and needs 8x fewer iterations, instead of 43 iterations of latency-bound launches.
+    A full 1024^2 frame gets the reference's (N, 8)."""
+    mult = max(1, min(8, (1 << 20) // max(N, 1)))
+    return (mult, 8 * mult)
+
+
+def _frame_buffers(dev, N, max_steps, budget):
+    """device workspace + pinned host mailbox of ntx_render_rays, cached per (device, stream, N, budget)"""
+    key = (dev.index, L.stream(), N, max_steps, budget)
     buf = _frame_cache.get(key)
     if buf is None:
-        ws = torch.empty(L.lib().ntx_render_rays_workspace_bytes(N) + 256, dtype=torch.uint8, device=dev)
+        ws = torch.empty(L.lib().ntx_render_rays_workspace_bytes(N, budget) + 256, dtype=torch.uint8, device=dev)
         off = (-ws.data_ptr()) % 256
         mailbox = torch.zeros(max_steps + 1, dtype=torch.int32).pin_memory()
         counter = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -101,14 +116,16 @@ def _aabb_tensor(bound, dev, cache={}):
 
 
 def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aabb=None, min_near=0.2, dt_gamma=0.0, max_steps=1024, bg_color=1.0,
-                perturb=0, count_samples=False, profile=None, use_mip=True, device_loop=True, mip=None):
+                perturb=0, count_samples=False, profile=None, use_mip=True, device_loop=True, mip=None, schedule="auto"):
     """Inference branch of NeRFRenderer.run_cuda (renderer.py:436-489).  rays_o/d [N,3] fp32 CUDA.
     Returns dict(image [N,3], depth [N], weights_sum [N], iterations, n_samples (if count_samples)).
     device_loop=True (default): the whole loop is ONE libntx call whose iteration state stays on the device (ntx_render_rays);
     device_loop=False: the reference's structure, one extension call per step and a blocking n_alive read per iteration
     (bit-identical results; kept for profiling and as the parity reference of the device-driven loop).
     profile: optional list (stepwise loop only); gets one (start_event, stop_event, live_sample_count_tensor) per field-kernel launch.
-    mip: optional pre-built occupancy mip (ntx_build_occupancy_mip) of density_bitfield."""
+    mip: optional pre-built occupancy mip (ntx_build_occupancy_mip) of density_bitfield.
+    schedule (device loop only): "auto" (auto_schedule(N); the reference's when perturb != 0), "reference", "wide", or a
+    (budget_multiple, max_n_step) pair — the image is the same either way, see include/ntx.h."""
     dev = rays_o.device
     rays_o = rays_o.contiguous().view(-1, 3).float()
     rays_d = rays_d.contiguous().view(-1, 3).float()
@@ -124,7 +141,11 @@ def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aab
         mip = None
     if device_loop and profile is None and N > 0:
         import ctypes
-        ws, ws_ptr, mailbox, counter = _frame_buffers(dev, N, int(max_steps))
+        if schedule == "auto":
+            schedule = "reference" if perturb else auto_schedule(N)
+        mult, cap = SCHEDULES[schedule] if isinstance(schedule, str) else schedule
+        budget = int(mult) * N
+        ws, ws_ptr, mailbox, counter = _frame_buffers(dev, N, int(max_steps), budget)
         image_c = torch.empty(N, 3, dtype=torch.float32, device=dev)
         depth_c = torch.empty(N, dtype=torch.float32, device=dev)
         wsum_c = torch.empty(N, dtype=torch.float32, device=dev)
@@ -132,7 +153,7 @@ def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aab
             counter.zero_()
         stats = (ctypes.c_uint32 * 2)()
         L.call("ntx_render_rays", L.ptr(rays_o), L.ptr(rays_d), N, L.ptr(aabb), float(min_near), float(bound), float(dt_gamma), int(max_steps), int(perturb),
-               int(cascade), int(grid_size), L.ptr(density_bitfield), None if mip is None else L.ptr(mip), L.ptr(field.table), L.ptr(field.offsets),
+               budget, int(cap), int(cascade), int(grid_size), L.ptr(density_bitfield), None if mip is None else L.ptr(mip), L.ptr(field.table), L.ptr(field.offsets),
                field.num_levels, field.S, field.H, int(field.align_corners), L.ptr(field.w_sigma), L.ptr(field.w_color), float(field.density_scale),
                L.ptr(wsum_c), L.ptr(depth_c), L.ptr(image_c), ws_ptr, mailbox.data_ptr(), counter.data_ptr() if count_samples else None,
                ctypes.addressof(stats), st)

@@ -117,7 +117,7 @@ def test_renderer_loop_on_dropin_ops_matches_fused_render_and_oracle():
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.half):
         image, depth, ws, iters = _run_cuda_inference(m, rays_o, rays_d, bits, 1, 128, 1.0)
     field = render.NGPField.from_modules(m.encoder, m.sigma_net, m.color_net, bound=1.0)
-    out = render.render_rays(field, rays_o, rays_d, bits, 1, 128, count_samples=True)
+    out = render.render_rays(field, rays_o, rays_d, bits, 1, 128, count_samples=True, schedule="reference")
     assert out["iterations"] == iters
     np.testing.assert_array_equal(out["image"].cpu().numpy(), image.cpu().numpy())
     np.testing.assert_array_equal(out["depth"].cpu().numpy(), depth.cpu().numpy())

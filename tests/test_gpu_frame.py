@@ -32,9 +32,30 @@ def test_device_driven_frame_equals_stepwise_loop(hw, cascade, grid_size, bound,
     ntx()
     render, field, rays_o, rays_d, bits = _scene(hw, cascade, grid_size, bound)
     a = render.render_rays(field, rays_o, rays_d, bits, cascade, grid_size, count_samples=True, device_loop=False, **kw)
-    b = render.render_rays(field, rays_o, rays_d, bits, cascade, grid_size, count_samples=True, device_loop=True, **kw)
+    b = render.render_rays(field, rays_o, rays_d, bits, cascade, grid_size, count_samples=True, device_loop=True, schedule="reference", **kw)
     assert a["iterations"] == b["iterations"] and a["iterations"] > 0
     assert a["n_samples"] == b["n_samples"] and a["n_samples"] > 0
+    for k in ("image", "depth", "weights_sum"):
+        np.testing.assert_array_equal(a[k].cpu().numpy(), b[k].cpu().numpy(), err_msg=k)
+
+
+@pytest.mark.parametrize("hw,cascade,grid_size,bound,kw", [
+    ((96, 96), 1, 128, 1.0, dict()),
+    ((57, 41), 1, 128, 1.0, dict(min_near=0.05)),
+    ((64, 64), 2, 64, 2.0, dict(dt_gamma=1.0 / 128)),
+], ids=["plain", "ragged", "cascades_dtgamma"])
+@pytest.mark.parametrize("schedule", ["wide", "auto", (2, 13), (8, 64)])
+def test_image_does_not_depend_on_the_sample_schedule(hw, cascade, grid_size, bound, kw, schedule):
+    """n_step = clamp(budget // n_alive, 1, cap) only decides how a ray's samples are spread over loop iterations: each ray
+    still composites the same samples in the same order and stops at the same one.  (More than 8 samples per ray and
+    iteration also exercises the chunked path of the marcher.)  perturb must be 0: the reference jitters t once per
+    march_rays CALL (raymarching.cu:1011), so with perturb the schedule is part of the random realisation."""
+    ntx()
+    render, field, rays_o, rays_d, bits = _scene(hw, cascade, grid_size, bound, seed=1)
+    a = render.render_rays(field, rays_o, rays_d, bits, cascade, grid_size, count_samples=True, schedule="reference", **kw)
+    b = render.render_rays(field, rays_o, rays_d, bits, cascade, grid_size, count_samples=True, schedule=schedule, **kw)
+    assert b["iterations"] < a["iterations"]
+    assert b["n_samples"] >= a["n_samples"]          # samples behind an opaque hit are marched (and discarded) in bigger chunks
     for k in ("image", "depth", "weights_sum"):
         np.testing.assert_array_equal(a[k].cpu().numpy(), b[k].cpu().numpy(), err_msg=k)
 
@@ -58,7 +79,7 @@ def test_render_rays_rejects_missing_workspace_and_mailbox():
     import ctypes
     it = (ctypes.c_uint32 * 2)()
     d = torch.zeros(16, device=DEV)
-    args = [d.data_ptr(), d.data_ptr(), 1, d.data_ptr(), 0.2, 1.0, 0.0, 8, 0, 1, 128, d.data_ptr(), None, d.data_ptr(), d.data_ptr(), 16, 0.5, 16, 1, d.data_ptr(),
+    args = [d.data_ptr(), d.data_ptr(), 1, d.data_ptr(), 0.2, 1.0, 0.0, 8, 0, 0, 0, 1, 128, d.data_ptr(), None, d.data_ptr(), d.data_ptr(), 16, 0.5, 16, 1, d.data_ptr(),
             d.data_ptr(), 1.0, d.data_ptr(), d.data_ptr(), d.data_ptr()]
     with pytest.raises(RuntimeError, match="workspace"):
         L.call("ntx_render_rays", *args, None, None, None, ctypes.addressof(it), L.stream())
