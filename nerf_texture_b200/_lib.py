@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libntx.so")
+LIB_PATH = os.environ.get("NTX_LIB_PATH") or os.path.join(_HERE, "lib", "libntx.so")   # NTX_LIB_PATH: development (tools/tune.py variants)
 _lib = None
 
 F32, F16, F64 = 0, 1, 2

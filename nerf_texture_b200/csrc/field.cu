@@ -28,15 +28,21 @@
 
 namespace ntx {
 
+#ifndef NTX_FIELD_PRODUCERS       // development sweeps: NTX_NVCC_EXTRA="-DNTX_FIELD_PRODUCERS=8 -DNTX_FIELD_STAGES=2"
+#define NTX_FIELD_PRODUCERS 12
+#endif
+#ifndef NTX_FIELD_STAGES
+#define NTX_FIELD_STAGES 3
+#endif
 constexpr int kConsumerWarps = 4;   // 4: one per TMEM lane quarter | 8: two per quarter, warp w reads lanes 32*(w&3).., columns 32*(w>>2)..
-constexpr int kProducerWarps = 12;
+constexpr int kProducerWarps = NTX_FIELD_PRODUCERS;
 constexpr int kTaskRows = 16;                                            // rows one producer warp gathers at a time
 constexpr int kTasksPerTile = 8;                                         // kTileRows / kTaskRows
 constexpr int kFieldThreads = 32 * (kConsumerWarps + kProducerWarps);   // 512
 constexpr int kFW = 64;          // hidden width of both MLPs
 constexpr int kColorIn = 32;     // SH(16) + geo_feat(15) + zero pad (network_ff.py:42,95-97)
 constexpr int kFieldMaxLevels = 32;
-constexpr int kStages = 3;       // feature tiles in the producer -> consumer ring
+constexpr int kStages = NTX_FIELD_STAGES;       // feature tiles in the producer -> consumer ring
 constexpr int kCtx = 1;          // tiles the consumers keep in flight (2 = ping-pong; measured slower)
 constexpr uint32_t kFieldTmemCols = 64 * kCtx;
 
