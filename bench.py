@@ -275,6 +275,15 @@ def main():
                             "tensor_note": "36864 FLOP/sample on tcgen05: %.1f TFLOP/s achieved inside the kernel" % (live * 36864 / kt / 1e12)}
         # ---- BASELINE config 2: 2^20 samples through the fused field kernel and the stand-alone encoder ------------
         line["cfg2"] = bench_cfg2(torch, L, field, device, peaks)
+        # ---- the reference's own CUDA kernels (rebuilt for sm_100a, oracle/_ref) on the same frame, when the build is present:
+        #      context for the headline only — the contract's reference arm (--impl reference) is the CPU oracle
+        if world == 1 and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "_ref_raymarching.so")):
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import compare_ref
+                line["reference_cuda"] = compare_ref.main(only_frame=True)
+            except Exception as e:      # never let the side measurement break the bench line
+                line["reference_cuda"] = {"unavailable": repr(e)[:200]}
         if not args.no_cpu_baseline and world == 1:
             v, dt, ns, cores, sample = cpu_render_sample(stride=5)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "seconds": dt}

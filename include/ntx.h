@@ -174,6 +174,9 @@ int ntx_ngp_field_forward(const float* xyz, const float* dirs, const float* delt
  *     and discarded, changes), so a B200 with memory to spare can run e.g. (4N, 32) and cut the number of iterations.
  *     Exceptions: perturb != 0 (the reference jitters t once per march_rays call, so the schedule is part of the random
  *     realisation) and rays that need more than max_steps samples (the step budget is checked once per iteration).
+ *   walk_budget: 0 = the reference's iteration structure.  > 0: after the first iteration a ray that has crossed this many empty
+ *     voxels in one march without filling its n_step slots pauses (sentinel (0, -t), see raymarch.cu) and carries on in the next
+ *     iteration from exactly that t: same samples, same image, but a launch no longer lasts as long as its longest walk.
  *   rays_o, rays_d [N,3] f32; aabb [6] f32 (device); grid = density bit-field; occupancy_mip nullable (ntx_build_occupancy_mip)
  *   weights_sum [N], depth [N], image [N,3] f32: overwritten (image WITHOUT the background term, like composite_rays)
  *   workspace: ntx_render_rays_workspace_bytes(N, sample_budget) bytes of device memory, 256-byte aligned
@@ -184,7 +187,7 @@ int ntx_ngp_field_forward(const float* xyz, const float* dirs, const float* delt
 size_t ntx_render_rays_workspace_bytes(uint32_t N, uint32_t sample_budget);
 int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const float* aabb, float min_near, float bound,
                     float dt_gamma, uint32_t max_steps, uint32_t perturb, uint32_t sample_budget, uint32_t max_n_step,
-                    uint32_t C, uint32_t H, const uint8_t* grid,
+                    uint32_t walk_budget, uint32_t C, uint32_t H, const uint8_t* grid,
                     const uint8_t* occupancy_mip, const void* embeddings_f16, const int* offsets, uint32_t L, float S,
                     uint32_t base_resolution, int align_corners, const void* w_sigma_f16, const void* w_color_f16,
                     float density_scale, float* weights_sum, float* depth, float* image, void* workspace,

@@ -677,15 +677,21 @@ __device__ __forceinline__ void block_copy_out(float* __restrict__ dst, const fl
 // Device-driven frames (ntx_render_rays): n_alive / n_step / M_padded of an iteration are only known on the device.  The
 // kernels of the inference loop then take them from a FrameState and the by-value arguments are just the launch bound.
 struct FrameState { int n_alive, n_step, m_padded, step; };
+// "Paused" sentinel of the device-driven loop: a ray that has walked `walk_budget` empty voxels in one launch without filling
+// its n_step slots stops there and writes (delta, delta_t) = (0, -t) into its next slot instead of (0, 0).  composite_rays then
+// keeps the ray alive with rays_t = t (exactly the t the marcher would have probed next), so the walk continues in the next
+// iteration instead of making the whole launch wait for the few rays that graze the object (the launch time of a steady-state
+// iteration was the latency of its longest walk).  The reference's marcher never writes a negative delta_t.
 
 __global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
     uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_alive, const float* __restrict__ rays_t, const float* __restrict__ rays_o,
     const float* __restrict__ rays_d, const float bound, const float dt_gamma, const uint32_t max_steps, const uint32_t C, const uint32_t H,
     const uint8_t* __restrict__ grid, const float* __restrict__ nears, const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs,
     float* __restrict__ deltas, const uint32_t perturb, uint32_t M_padded, const uint8_t* __restrict__ coarse, const FrameState* __restrict__ state,
-    unsigned long long* __restrict__ sample_counter) {
+    unsigned long long* __restrict__ sample_counter, uint32_t walk_budget) {
     extern __shared__ __align__(16) float stage[];          // [128*nc*3] xyz | [128*nc*3] dir | [128*nc*2] delta, nc = min(n_step, 8)
     if (state) { n_alive = (uint32_t)state->n_alive; n_step = (uint32_t)state->n_step; M_padded = (uint32_t)state->m_padded; }
+    if (!state || state->step == 0 || walk_budget == 0) walk_budget = 0xffffffffu;   // the approach to the object (first iteration) is walked in one go
     const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
     {   // padding rows beyond n_alive*n_step (align-to-128 tail, raymarching.py:386-387)
         const uint32_t row = n_alive * n_step + n;
@@ -722,6 +728,7 @@ __global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
         last_t = t;
     }
     uint32_t emitted = 0, empties = 0;
+    bool paused = false;
     // The ray's n_step output rows are produced in chunks of at most 8 (the reference never asks for more than 8; wider
     // schedules of ntx_render_rays do): a chunk is staged in shared memory and written out before the next one starts.
     for (uint32_t c0 = 0; c0 < n_step; c0 += kMarchMaxStagedSteps) {
@@ -777,14 +784,23 @@ __global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
                         pl[0] = dt; pl[1] = t - last_t;
                         last_t = t;
                         px += 3; pd += 3; pl += 2; step++;
-                    } else if (coarse && ((empties++ & 3u) == 0u)) {
-                        // in empty space: if nothing occupied can be reached any more, this ray emits no further sample and is dead
-                        // after composite_rays whatever t it stops at — skip the voxel-by-voxel walk to `far`
-                        if (!maybe_occupied_ahead(r, p, coarse, t, far)) { far = t; break; }
+                    } else {
+                        // (probe() has advanced t to the next voxel)
+                        if (coarse && ((empties & 3u) == 0u)) {
+                            // in empty space: if nothing occupied can be reached any more, this ray emits no further sample and is
+                            // dead after composite_rays whatever t it stops at — skip the voxel-by-voxel walk to `far`
+                            if (!maybe_occupied_ahead(r, p, coarse, t, far)) { far = t; break; }
+                        }
+                        if (++empties > walk_budget && t < far) { paused = true; break; }
                     }
                 }
-                if (step < nc) exhausted = true;                 // ran out of ray: every later slot is a sentinel
+                if (step < nc) exhausted = true;                 // ran out of ray (or paused): every later slot is a sentinel
                 emitted += step;
+                if (paused) {                                    // step < nc here: the pause happens on an empty probe
+                    px[0] = 0; px[1] = 0; px[2] = 0; pd[0] = 0; pd[1] = 0; pd[2] = 0; pl[0] = 0; pl[1] = -t;
+                    px += 3; pd += 3; pl += 2; step++;
+                    paused = false;
+                }
             }
             for (; step < nc; step++) {                          // unused slots: zero (delta == 0 is composite_rays' stop sentinel)
                 px[0] = 0; px[1] = 0; px[2] = 0; pd[0] = 0; pd[1] = 0; pd[2] = 0; pl[0] = 0; pl[1] = 0;
@@ -837,8 +853,12 @@ __global__ void __launch_bounds__(128) composite_rays_kernel(uint32_t n_alive, u
     float weight_sum = weights_sum[index], d = depth[index];
     float r = image[(size_t)index * 3], g = image[(size_t)index * 3 + 1], b = image[(size_t)index * 3 + 2];
     uint32_t step = 0;
+    bool paused = false;
     while (step < n_step) {
-        if (deltas[0] == 0) break;
+        if (deltas[0] == 0) {
+            if (deltas[1] < 0) { t = -deltas[1]; paused = true; }   // paused by the device-driven marcher: resume at exactly this t
+            break;
+        }
         const float alpha = 1.0f - __expf(-sigmas[0] * deltas[0]);
         const float T = 1 - weight_sum;
         const float weight = alpha * T;
@@ -849,7 +869,7 @@ __global__ void __launch_bounds__(128) composite_rays_kernel(uint32_t n_alive, u
         if (T < 1e-4) break;   // double literal on purpose (:1081)
         sigmas++; rgbs += 3; deltas += 2; step++;
     }
-    rays_t[n] = (step < n_step) ? -1.0f : t;
+    rays_t[n] = (step < n_step && !paused) ? -1.0f : t;
     weights_sum[index] = weight_sum; depth[index] = d;
     image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
 }
@@ -1006,7 +1026,7 @@ extern "C" int ntx_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays
         const size_t smem = (size_t)kMarchThreads * min(n_step, kMarchMaxStagedSteps) * 8 * sizeof(float);
         march_rays_staged_kernel<<<ceil_div<uint32_t>(threads, kMarchThreads), kMarchThreads, smem, ST(stream)>>>(
             n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs, dirs, deltas, perturb, M_padded,
-            occupancy_mip, nullptr, nullptr);
+            occupancy_mip, nullptr, nullptr, 0);
         return check_launch("march_rays");
     }
     march_rays_kernel<<<ceil_div<uint32_t>(threads, 128), 128, 0, ST(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid,
@@ -1101,7 +1121,8 @@ extern "C" size_t ntx_render_rays_workspace_bytes(uint32_t N, uint32_t sample_bu
 }
 
 extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const float* aabb, float min_near, float bound, float dt_gamma,
-                               uint32_t max_steps, uint32_t perturb, uint32_t sample_budget, uint32_t max_n_step, uint32_t C, uint32_t H, const uint8_t* grid,
+                               uint32_t max_steps, uint32_t perturb, uint32_t sample_budget, uint32_t max_n_step, uint32_t walk_budget, uint32_t C, uint32_t H,
+                               const uint8_t* grid,
                                const uint8_t* occupancy_mip,
                                const void* embeddings_f16, const int* offsets, uint32_t L, float S, uint32_t base_resolution, int align_corners,
                                const void* w_sigma_f16, const void* w_color_f16, float density_scale, float* weights_sum, float* depth, float* image,
@@ -1154,7 +1175,7 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
         // padding rows (at most 128) are cleared by the first threads of the launch: at least one block
         march_rays_staged_kernel<<<ceil_div<uint32_t>(max(bound_rays, 128u), kMarchThreads), kMarchThreads, march_smem, st>>>(
             bound_rays, 1, w.rays_alive[cur], w.rays_t[cur], rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, w.nears, w.fars, w.xyzs, w.dirs, w.deltas, perturb, 0,
-            occupancy_mip, s_cur, sample_counter);
+            occupancy_mip, s_cur, sample_counter, walk_budget);
         const uint32_t m_bound = (uint32_t)min((uint64_t)max(N, sample_budget), (uint64_t)bound_rays * max_n_step) + 128u;
         const int rc = launch_ngp_field(w.xyzs, w.dirs, w.deltas, m_bound, &s_cur->m_padded, bound, embeddings_f16, offsets, L, S, base_resolution, align_corners,
                                         w_sigma_f16, w_color_f16, density_scale, w.sigmas, w.rgbs, st);

@@ -85,6 +85,9 @@ SCHEDULES = {
 }
 
 
+WALK_BUDGET = 16   # empty voxels a ray may cross per march before it pauses (ntx_render_rays, walk_budget); 0 = never pause
+
+
 def auto_schedule(N):
     """Keep about 2^20 sample rows per iteration whatever the number of rays: a rank that renders 1/8 of a frame marches 8x
     more samples per ray and iteration and needs 8x fewer iterations, instead of 43 iterations of latency-bound launches.
@@ -141,6 +144,7 @@ def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aab
         mip = None
     if device_loop and profile is None and N > 0:
         import ctypes
+        walk = 0 if (schedule == "reference" or perturb) else WALK_BUDGET   # "reference" = the reference's exact iteration structure
         if schedule == "auto":
             schedule = "reference" if perturb else auto_schedule(N)
         mult, cap = SCHEDULES[schedule] if isinstance(schedule, str) else schedule
@@ -153,7 +157,7 @@ def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aab
             counter.zero_()
         stats = (ctypes.c_uint32 * 2)()
         L.call("ntx_render_rays", L.ptr(rays_o), L.ptr(rays_d), N, L.ptr(aabb), float(min_near), float(bound), float(dt_gamma), int(max_steps), int(perturb),
-               budget, int(cap), int(cascade), int(grid_size), L.ptr(density_bitfield), None if mip is None else L.ptr(mip), L.ptr(field.table), L.ptr(field.offsets),
+               budget, int(cap), walk, int(cascade), int(grid_size), L.ptr(density_bitfield), None if mip is None else L.ptr(mip), L.ptr(field.table), L.ptr(field.offsets),
                field.num_levels, field.S, field.H, int(field.align_corners), L.ptr(field.w_sigma), L.ptr(field.w_color), float(field.density_scale),
                L.ptr(wsum_c), L.ptr(depth_c), L.ptr(image_c), ws_ptr, mailbox.data_ptr(), counter.data_ptr() if count_samples else None,
                ctypes.addressof(stats), st)

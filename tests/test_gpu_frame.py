@@ -44,7 +44,7 @@ def test_device_driven_frame_equals_stepwise_loop(hw, cascade, grid_size, bound,
     ((57, 41), 1, 128, 1.0, dict(min_near=0.05)),
     ((64, 64), 2, 64, 2.0, dict(dt_gamma=1.0 / 128)),
 ], ids=["plain", "ragged", "cascades_dtgamma"])
-@pytest.mark.parametrize("schedule", ["wide", "auto", (2, 13), (8, 64)])
+@pytest.mark.parametrize("schedule", ["wide", "auto", (1, 8), (2, 13), (8, 64)])
 def test_image_does_not_depend_on_the_sample_schedule(hw, cascade, grid_size, bound, kw, schedule):
     """n_step = clamp(budget // n_alive, 1, cap) only decides how a ray's samples are spread over loop iterations: each ray
     still composites the same samples in the same order and stops at the same one.  (More than 8 samples per ray and
@@ -54,7 +54,8 @@ def test_image_does_not_depend_on_the_sample_schedule(hw, cascade, grid_size, bo
     render, field, rays_o, rays_d, bits = _scene(hw, cascade, grid_size, bound, seed=1)
     a = render.render_rays(field, rays_o, rays_d, bits, cascade, grid_size, count_samples=True, schedule="reference", **kw)
     b = render.render_rays(field, rays_o, rays_d, bits, cascade, grid_size, count_samples=True, schedule=schedule, **kw)
-    assert b["iterations"] < a["iterations"]
+    if schedule != (1, 8):                            # (1, 8) = the reference's n_step rule, only the walk budget differs
+        assert b["iterations"] < a["iterations"]
     assert b["n_samples"] >= a["n_samples"]          # samples behind an opaque hit are marched (and discarded) in bigger chunks
     for k in ("image", "depth", "weights_sum"):
         np.testing.assert_array_equal(a[k].cpu().numpy(), b[k].cpu().numpy(), err_msg=k)
@@ -79,7 +80,7 @@ def test_render_rays_rejects_missing_workspace_and_mailbox():
     import ctypes
     it = (ctypes.c_uint32 * 2)()
     d = torch.zeros(16, device=DEV)
-    args = [d.data_ptr(), d.data_ptr(), 1, d.data_ptr(), 0.2, 1.0, 0.0, 8, 0, 0, 0, 1, 128, d.data_ptr(), None, d.data_ptr(), d.data_ptr(), 16, 0.5, 16, 1, d.data_ptr(),
+    args = [d.data_ptr(), d.data_ptr(), 1, d.data_ptr(), 0.2, 1.0, 0.0, 8, 0, 0, 0, 0, 1, 128, d.data_ptr(), None, d.data_ptr(), d.data_ptr(), 16, 0.5, 16, 1, d.data_ptr(),
             d.data_ptr(), 1.0, d.data_ptr(), d.data_ptr(), d.data_ptr()]
     with pytest.raises(RuntimeError, match="workspace"):
         L.call("ntx_render_rays", *args, None, None, None, ctypes.addressof(it), L.stream())

@@ -45,9 +45,8 @@ def time_it(fn, iters=10, warm=3, flush=None):
     return ts[len(ts) // 2]
 
 
-def main():
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
+def main(only_frame=False):
+    dev = torch.device("cuda", torch.cuda.current_device())
     G, F, S, R = ref("gridencoder"), ref("ffmlp"), ref("shencoder"), ref("raymarching")
     F.allocate_splitk(4)
     field, rays_o, rays_d, bits = bench.build_scene(dev)
@@ -74,6 +73,18 @@ def main():
         F.ffmlp_inference(cin, field.w_color, M, 32, 16, 64, 3, 0, 6, buf, hc)
         return sigma, torch.sigmoid(hc[:, :3]).float()
 
+    res = {}
+    if not only_frame:
+        res.update(_config2(dev, field, flush, ref_field, G, F))
+    res.update(_config3(dev, field, rays_o, rays_d, bits, flush, ref_field, R))
+    res["note"] = ("reference_cuda = /root/reference's gridencoder/ffmlp/shencoder/raymarching .cu rebuilt unmodified for sm_100a (oracle/_ref), driven like its "
+                   "Python drives them; median of 5-10 timed runs, L2 flushed before each; same B200, same inputs")
+    return res
+
+
+def _config2(dev, field, flush, ref_field, G, F):
+    nlev = field.num_levels
+    dummy_h = torch.empty(1, dtype=torch.half, device=dev)
     res = {}
     # ---------------- config 2: 2^20 samples through the field --------------------------------------------------------
     B = 1 << 20
@@ -108,6 +119,12 @@ def main():
     res["cfg2_ffmlp_32_64_64_16_2^20"] = {"reference_cuda_ms": t_ref, "ntx_ms": t_ntx, "speedup": t_ref / t_ntx,
                                           "max_abs_diff": float((h_ref.float() - h_ntx.float()).abs().max())}
 
+    return res
+
+
+def _config3(dev, field, rays_o, rays_d, bits, flush, ref_field, R):
+    bound = field.bound
+    res = {}
     # ---------------- config 3: the 1024x1024 frame ------------------------------------------------------------------
     N = rays_o.shape[0]
     aabb = torch.tensor([-bound] * 3 + [bound] * 3, dtype=torch.float32, device=dev)
@@ -152,10 +169,9 @@ def main():
                                    "reference_gsamples_per_s": o["n_samples"] / t_ref / 1e6, "ntx_gsamples_per_s": o["n_samples"] / t_ntx / 1e6,
                                    "iterations": [it_r, o["iterations"]], "max_abs_image_diff": float((img_r - o["image"]).abs().max()),
                                    "max_abs_depth_diff": float((dep_r - o["depth"]).abs().max())}
-    res["note"] = ("reference_cuda = /root/reference's gridencoder/ffmlp/shencoder/raymarching .cu rebuilt unmodified for sm_100a (oracle/_ref), driven like its "
-                   "Python drives them; median of 5-10 timed runs, L2 flushed before each; same B200, same inputs")
-    print(json.dumps(res))
+    return res
 
 
 if __name__ == "__main__":
-    main()
+    torch.cuda.set_device(0)
+    print(json.dumps(main()))
