@@ -69,7 +69,7 @@ inline int resident_ctas_per_sm(const void* func, int threads, size_t dyn_smem, 
     return std::max(n, 1);
 }
 // field.cu: the fused field kernel, callable from the device-driven frame loop in raymarch.cu
-int launch_ngp_field(const float* xyz, const float* dirs, const float* deltas, uint32_t M, const int* M_dev, float bound, const void* embeddings_f16,
+int launch_ngp_field(const float* xyz, const float* dirs, const float* deltas, uint32_t M, const int* M_dev, const int* rows, float bound, const void* embeddings_f16,
                      const int* offsets, uint32_t L, float S, uint32_t H, int align_corners, const void* w_sigma_f16, const void* w_color_f16,
                      float density_scale, float* sigmas, float* rgbs, cudaStream_t stream);
 

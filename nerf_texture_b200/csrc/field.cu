@@ -129,7 +129,7 @@ __device__ __forceinline__ void field_issue_stage(uint32_t st, uint32_t ns, uint
 
 __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
     const float* __restrict__ xyz, const float* __restrict__ dirs, const float* __restrict__ deltas, const uint32_t M_arg, const int* __restrict__ M_dev,
-    const float bound, const __half* __restrict__ table, const int* __restrict__ offsets, const uint32_t L, const float S, const uint32_t H, const bool align,
+    const int* __restrict__ rows, const float bound, const __half* __restrict__ table, const int* __restrict__ offsets, const uint32_t L, const float S, const uint32_t H, const bool align,
     const __half* __restrict__ w_sigma, const __half* __restrict__ w_color, const uint32_t ns, const uint32_t nc, const float density_scale,
     float* __restrict__ sigmas, float* __restrict__ rgbs, const uint32_t dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -188,8 +188,9 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
             if (tile >= ntiles) break;
             const uint32_t s = k % kStages, use = k / kStages;
             const uint32_t srow = (task % kTasksPerTile) * kTaskRows + (lane >> 1);   // row of this lane pair inside the tile
-            const uint32_t b = tile * kTileRows + srow;
-            const bool valid = b < M;
+            const uint32_t bi = tile * kTileRows + srow;
+            const bool valid = bi < M;
+            const uint32_t b = (valid && rows) ? (uint32_t)rows[bi] : bi;     // row list of a device-driven frame: only rows the marcher filled
             float x = 0.f, y = 0.f, z = 0.f;
             bool skip = !valid;
             if (valid) {
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
         for (uint32_t k0 = 0;; k0 += kCtx) {
             if (blockIdx.x + k0 * gridDim.x >= ntiles) break;
             uint32_t b[kCtx];
-            bool has[kCtx], dead[kCtx];
+            bool has[kCtx], dead[kCtx], ok[kCtx];        // ok: this thread's row exists (ragged last tile)
             float dx[kCtx], dy[kCtx], dz[kCtx];   // view direction of this row: its SH basis is evaluated between the two nets
             // ---------------- take up to kCtx feature tiles and start their first layer --------------------------
 #pragma unroll
@@ -241,11 +242,13 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
                 const uint32_t k = k0 + c, tile = blockIdx.x + k * gridDim.x;
                 has[c] = tile < ntiles;
                 b[c] = tile * kTileRows + row;
-                dead[c] = true; dx[c] = dy[c] = dz[c] = 0.f;
+                dead[c] = true; ok[c] = false; dx[c] = dy[c] = dz[c] = 0.f;
                 if (!has[c]) continue;
                 const uint32_t s = k % kStages, use = k / kStages;
-                dead[c] = (b[c] >= M) || (deltas && deltas[(size_t)b[c] * 2] == 0.0f);
-                if (b[c] < M) { dx[c] = dirs[(size_t)b[c] * 3]; dy[c] = dirs[(size_t)b[c] * 3 + 1]; dz[c] = dirs[(size_t)b[c] * 3 + 2]; }
+                ok[c] = b[c] < M;
+                if (ok[c] && rows) b[c] = (uint32_t)rows[b[c]];
+                dead[c] = !ok[c] || (deltas && deltas[(size_t)b[c] * 2] == 0.0f);
+                if (ok[c]) { dx[c] = dirs[(size_t)b[c] * 3]; dy[c] = dirs[(size_t)b[c] * 3 + 1]; dz[c] = dirs[(size_t)b[c] * 3 + 2]; }
                 PROBE_MARK(2)
                 // Only the issuing thread waits for the feature tile: nobody else reads it, and a consumer warp still polling
                 // full_bar[s] after the slot has been released below could see the producers complete the NEXT phase of that
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
 #ifdef NTX_DEV_PROBES
                 if (dbg & 2u) {   // producer-only timing: release the slot at once, skip both MLPs
                     if (tid == 0) tc::mbar_arrive(&empty_bar[s]);
-                    if (b[c] < M) { st_stream_f32(sigmas + b[c], 0.f); for (int q = 0; q < 3; q++) st_stream_f32(rgbs + (size_t)b[c] * 3 + q, 0.f); }
+                    if (ok[c]) { st_stream_f32(sigmas + b[c], 0.f); for (int q = 0; q < 3; q++) st_stream_f32(rgbs + (size_t)b[c] * 3 + q, 0.f); }
                     has[c] = false;
                     continue;
                 }
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
 #pragma unroll
                         for (int j = 0; j < 8; j++) hb[j] = float2_to_half2_bits(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
                         const float h0 = __low2float(*reinterpret_cast<const __half2*>(&hb[0]));
-                        if (b[c] < M) st_stream_f32(sigmas + b[c], dead[c] ? 0.0f : density_scale * expf(h0));
+                        if (ok[c]) st_stream_f32(sigmas + b[c], dead[c] ? 0.0f : density_scale * expf(h0));
                         // colour-net input [128 x 32] = SH(dir) ++ h[1..15] ++ 0   (network_ff.py:93-97), built at the start of this
                         // tile's activation buffer: the hidden activations there are dead (the output-layer MMA has completed),
                         // and the colour net's first epilogue overwrites it only after its MMA has read it.
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
                     } else if (st + 1 == nst) {
                         uint32_t v[8];
                         if (lead) { tc::tmem_ld_x8(acc + ((quarter * 32u) << 16), v); tc::tmem_wait_ld(); }
-                        if (lead && b[c] < M) {
+                        if (lead && ok[c]) {
 #pragma unroll
                             for (int q = 0; q < 3; q++) {
                                 // rgb = sigmoid(h) evaluated on the fp16 output in fp32 and rounded back to fp16 (torch.sigmoid on a half tensor)
@@ -375,12 +378,14 @@ static uint32_t dev_probe_flags() {
 extern "C" int ntx_ngp_field_forward(const float* xyz, const float* dirs, const float* deltas, uint32_t M, float bound, const void* embeddings_f16,
                                      const int* offsets, uint32_t L, float S, uint32_t H, int align_corners, const void* w_sigma_f16,
                                      const void* w_color_f16, float density_scale, float* sigmas, float* rgbs, ntx_stream_t stream) {
-    return launch_ngp_field(xyz, dirs, deltas, M, nullptr, bound, embeddings_f16, offsets, L, S, H, align_corners, w_sigma_f16, w_color_f16, density_scale, sigmas,
+    return launch_ngp_field(xyz, dirs, deltas, M, nullptr, nullptr, bound, embeddings_f16, offsets, L, S, H, align_corners, w_sigma_f16, w_color_f16, density_scale, sigmas,
                             rgbs, reinterpret_cast<cudaStream_t>(stream));
 }
 
-// M = upper bound of the sample count (sizes the grid); M_dev (nullable, device) = the actual count, read by the kernel
-int ntx::launch_ngp_field(const float* xyz, const float* dirs, const float* deltas, uint32_t M, const int* M_dev, float bound, const void* embeddings_f16,
+// M = upper bound of the sample count (sizes the grid); M_dev (nullable, device) = the actual count, read by the kernel;
+// rows (nullable, device) = indices of the rows to evaluate (then M counts list entries)
+int ntx::launch_ngp_field(const float* xyz, const float* dirs, const float* deltas, uint32_t M, const int* M_dev, const int* rows, float bound,
+                          const void* embeddings_f16,
                           const int* offsets, uint32_t L, float S, uint32_t H, int align_corners, const void* w_sigma_f16, const void* w_color_f16,
                           float density_scale, float* sigmas, float* rgbs, cudaStream_t stream) {
     NTX_REQUIRE(xyz && dirs && embeddings_f16 && offsets && w_sigma_f16 && w_color_f16 && sigmas && rgbs, NTX_ERR_INVALID_ARGUMENT, "ngp_field_forward: null pointer");
@@ -409,7 +414,7 @@ int ntx::launch_ngp_field(const float* xyz, const float* dirs, const float* delt
     const uint32_t ntiles = ceil_div<uint32_t>(M, kTileRows);
     const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)(occ * sms));
     ngp_field_kernel<<<grid, kFieldThreads, plan.total, stream>>>(
-        xyz, dirs, deltas, M, M_dev, bound, static_cast<const __half*>(embeddings_f16), offsets, L, S, H, align_corners != 0,
+        xyz, dirs, deltas, M, M_dev, rows, bound, static_cast<const __half*>(embeddings_f16), offsets, L, S, H, align_corners != 0,
         static_cast<const __half*>(w_sigma_f16), static_cast<const __half*>(w_color_f16), ns, nc, density_scale, sigmas, rgbs, dev_probe_flags());
     return check_launch("ngp_field_forward");
 }

@@ -676,19 +676,19 @@ __device__ __forceinline__ void block_copy_out(float* __restrict__ dst, const fl
 
 // Device-driven frames (ntx_render_rays): n_alive / n_step / M_padded of an iteration are only known on the device.  The
 // kernels of the inference loop then take them from a FrameState and the by-value arguments are just the launch bound.
-struct FrameState { int n_alive, n_step, m_padded, step; };
+struct FrameState { int n_alive, n_step, m_padded, step, n_live, pad0, pad1, pad2; };   // n_live: rows the marcher filled this iteration
 // "Paused" sentinel of the device-driven loop: a ray that has walked `walk_budget` empty voxels in one launch without filling
 // its n_step slots stops there and writes (delta, delta_t) = (0, -t) into its next slot instead of (0, 0).  composite_rays then
 // keeps the ray alive with rays_t = t (exactly the t the marcher would have probed next), so the walk continues in the next
 // iteration instead of making the whole launch wait for the few rays that graze the object (the launch time of a steady-state
 // iteration was the latency of its longest walk).  The reference's marcher never writes a negative delta_t.
 
-__global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
+__global__ void __launch_bounds__(kMarchThreads, 6) march_rays_staged_kernel(
     uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_alive, const float* __restrict__ rays_t, const float* __restrict__ rays_o,
     const float* __restrict__ rays_d, const float bound, const float dt_gamma, const uint32_t max_steps, const uint32_t C, const uint32_t H,
     const uint8_t* __restrict__ grid, const float* __restrict__ nears, const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs,
     float* __restrict__ deltas, const uint32_t perturb, uint32_t M_padded, const uint8_t* __restrict__ coarse, const FrameState* __restrict__ state,
-    unsigned long long* __restrict__ sample_counter, uint32_t walk_budget) {
+    unsigned long long* __restrict__ sample_counter, uint32_t walk_budget, int* __restrict__ live_rows, int* __restrict__ live_counter) {
     extern __shared__ __align__(16) float stage[];          // [128*nc*3] xyz | [128*nc*3] dir | [128*nc*2] delta, nc = min(n_step, 8)
     if (state) { n_alive = (uint32_t)state->n_alive; n_step = (uint32_t)state->n_step; M_padded = (uint32_t)state->m_padded; }
     if (!state || state->step == 0 || walk_budget == 0) walk_budget = 0xffffffffu;   // the approach to the object (first iteration) is walked in one go
@@ -739,7 +739,7 @@ __global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
         float* px = sx + threadIdx.x * nc * 3;
         float* pd = sd + threadIdx.x * nc * 3;
         float* pl = sl + threadIdx.x * nc * 2;
-        uint32_t step = 0;
+        uint32_t step = 0, filled = 0;                           // filled: real samples of this chunk (no sentinels)
         if (mine) {
             float x, y, z, dt;
             if (!exhausted) {
@@ -796,6 +796,7 @@ __global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
                 }
                 if (step < nc) exhausted = true;                 // ran out of ray (or paused): every later slot is a sentinel
                 emitted += step;
+                filled = step;
                 if (paused) {                                    // step < nc here: the pause happens on an empty probe
                     px[0] = 0; px[1] = 0; px[2] = 0; pd[0] = 0; pd[1] = 0; pd[2] = 0; pl[0] = 0; pl[1] = -t;
                     px += 3; pd += 3; pl += 2; step++;
@@ -806,6 +807,18 @@ __global__ void __launch_bounds__(kMarchThreads) march_rays_staged_kernel(
                 px[0] = 0; px[1] = 0; px[2] = 0; pd[0] = 0; pd[1] = 0; pd[2] = 0; pl[0] = 0; pl[1] = 0;
                 px += 3; pd += 3; pl += 2;
             }
+        }
+        if (live_rows) {
+            // Row list for the field kernel: the rows this block filled, in ray order; blocks append in arrival order (the list is
+            // consumed 128 rows at a time, so locality between consecutive samples of a ray and neighbouring rays is preserved).
+            __shared__ uint32_t s_scan[33];
+            __shared__ uint32_t s_base;
+            uint32_t total;
+            const uint32_t excl = block_exclusive_scan(filled, total, s_scan);
+            if (threadIdx.x == 0) s_base = total ? (uint32_t)atomicAdd(live_counter, (int)total) : 0u;
+            __syncthreads();
+            const uint32_t row = n * n_step + c0;
+            for (uint32_t j = 0; j < filled; j++) live_rows[s_base + excl + j] = (int)(row + j);
         }
         __syncthreads();
         if (nc == n_step) {
@@ -918,6 +931,7 @@ __global__ void __launch_bounds__(kCompactThreads) compact_rays_kernel(uint32_t 
             s.n_step = s.n_alive ? (int)max(min(budget / (uint32_t)s.n_alive, max_n_step), 1u) : 0;   // renderer.py:464 with (N, 8)
             const uint32_t m = (uint32_t)s.n_alive * (uint32_t)s.n_step;
             s.m_padded = s.n_alive ? (int)(m + 128u - (m % 128u)) : 0;         // raymarching.py:386-387 (align = 128)
+            s.n_live = 0; s.pad0 = s.pad1 = s.pad2 = 0;
             *state_out = s;
             if (host_mailbox) { *host_mailbox = s.n_alive; __threadfence_system(); }
         } else {
@@ -1026,7 +1040,7 @@ extern "C" int ntx_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays
         const size_t smem = (size_t)kMarchThreads * min(n_step, kMarchMaxStagedSteps) * 8 * sizeof(float);
         march_rays_staged_kernel<<<ceil_div<uint32_t>(threads, kMarchThreads), kMarchThreads, smem, ST(stream)>>>(
             n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs, dirs, deltas, perturb, M_padded,
-            occupancy_mip, nullptr, nullptr, 0);
+            occupancy_mip, nullptr, nullptr, 0, nullptr, nullptr);
         return check_launch("march_rays");
     }
     march_rays_kernel<<<ceil_div<uint32_t>(threads, 128), 128, 0, ST(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid,
@@ -1084,6 +1098,7 @@ __global__ void __launch_bounds__(256) frame_init_kernel(const uint32_t N, const
         s.step = 0; s.n_alive = (int)N; s.n_step = (int)max(min(budget / N, max_n_step), 1u);   // N // N = 1 for the reference schedule
         const uint32_t m = N * (uint32_t)s.n_step;
         s.m_padded = (int)(m + 128u - (m % 128u));
+        s.n_live = 0; s.pad0 = s.pad1 = s.pad2 = 0;
         *state = s;
         if (host_mailbox) { *host_mailbox = (int)N; __threadfence_system(); }
     }
@@ -1092,6 +1107,7 @@ __global__ void __launch_bounds__(256) frame_init_kernel(const uint32_t N, const
 struct FrameWorkspace {
     float *nears, *fars, *rays_t[2], *xyzs, *dirs, *deltas, *sigmas, *rgbs;
     int* rays_alive[2];
+    int* live_rows;
     FrameState* state;     // [2]
     ScanWS* scan;
     size_t bytes;
@@ -1111,6 +1127,7 @@ static FrameWorkspace carve_frame_workspace(void* base, uint32_t N, uint32_t bud
     w.deltas = static_cast<float*>(take(sizeof(float) * 2 * Mmax));
     w.sigmas = static_cast<float*>(take(sizeof(float) * Mmax));
     w.rgbs = static_cast<float*>(take(sizeof(float) * 3 * Mmax));
+    w.live_rows = static_cast<int*>(take(sizeof(int) * Mmax));
     w.bytes = off;
     return w;
 }
@@ -1175,10 +1192,11 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
         // padding rows (at most 128) are cleared by the first threads of the launch: at least one block
         march_rays_staged_kernel<<<ceil_div<uint32_t>(max(bound_rays, 128u), kMarchThreads), kMarchThreads, march_smem, st>>>(
             bound_rays, 1, w.rays_alive[cur], w.rays_t[cur], rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, w.nears, w.fars, w.xyzs, w.dirs, w.deltas, perturb, 0,
-            occupancy_mip, s_cur, sample_counter, walk_budget);
+            occupancy_mip, s_cur, sample_counter, walk_budget, w.live_rows, &s_cur->n_live);
         const uint32_t m_bound = (uint32_t)min((uint64_t)max(N, sample_budget), (uint64_t)bound_rays * max_n_step) + 128u;
-        const int rc = launch_ngp_field(w.xyzs, w.dirs, w.deltas, m_bound, &s_cur->m_padded, bound, embeddings_f16, offsets, L, S, base_resolution, align_corners,
-                                        w_sigma_f16, w_color_f16, density_scale, w.sigmas, w.rgbs, st);
+        // the field runs over the list of rows the marcher filled (no tile is spent on sentinel rows)
+        const int rc = launch_ngp_field(w.xyzs, w.dirs, nullptr, m_bound, &s_cur->n_live, w.live_rows, bound, embeddings_f16, offsets, L, S, base_resolution,
+                                        align_corners, w_sigma_f16, w_color_f16, density_scale, w.sigmas, w.rgbs, st);
         if (rc != NTX_OK) return rc;
         composite_rays_kernel<<<ceil_div<uint32_t>(bound_rays, 128), 128, 0, st>>>(bound_rays, 1, w.rays_alive[cur], w.rays_t[cur], w.sigmas, w.rgbs, w.deltas, weights_sum,
                                                                                   depth, image, s_cur);
