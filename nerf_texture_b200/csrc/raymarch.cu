@@ -747,6 +747,8 @@ __global__ void __launch_bounds__(kMarchThreads, 6) march_rays_staged_kernel(
                 // (the same float additions the sequential marcher performs).  Issue all their occupancy loads at once instead
                 // of one dependent load per step, then accept the longest all-occupied prefix; the first empty voxel falls back
                 // to the sequential loop below at exactly the state the reference would be in.
+                // The speculated samples are written into their slots right away (a slot that turns out not to be reached is
+                // overwritten by the sequential loop or the zero fill), so accepting a prefix costs one bit test per sample.
                 float tq[kMarchMaxStagedSteps];
                 uint32_t bitidx[kMarchMaxStagedSteps], byte[kMarchMaxStagedSteps];
                 float tcur = t;
@@ -758,24 +760,23 @@ __global__ void __launch_bounds__(kMarchThreads, 6) march_rays_staged_kernel(
                         const uint32_t index = locate(r, p, tcur, x, y, z, dt);
                         bitidx[s] = index & 7u;
                         byte[s] = p.grid[index >> 3];
-                        tcur += dt;
+                        px[3 * s] = x; px[3 * s + 1] = y; px[3 * s + 2] = z;
+                        pd[3 * s] = r.dx; pd[3 * s + 1] = r.dy; pd[3 * s + 2] = r.dz;
+                        const float t_end = tcur + dt;                 // == the sequential marcher's `t += dt`
+                        pl[2 * s] = dt; pl[2 * s + 1] = t_end - (s == 0 ? last_t : tcur);   // last_t of sample s > 0 is the end of sample s-1 = tcur
+                        tcur = t_end;
                         nspec = s + 1;
                     }
                 }
+                bool run = true;
 #pragma unroll
                 for (uint32_t s = 0; s < kMarchMaxStagedSteps; s++) {
-                    if (s < nspec && step == s) {                     // step == s: all earlier speculated probes were occupied
-                        if (byte[s] & (1u << bitidx[s])) {
-                            locate(r, p, tq[s], x, y, z, dt);
-                            px[0] = x; px[1] = y; px[2] = z;
-                            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
-                            t = tq[s] + dt;
-                            pl[0] = dt; pl[1] = t - last_t;
-                            last_t = t;
-                            px += 3; pd += 3; pl += 2; step++;
-                        }
+                    if (s < nspec && run) {                            // run: all earlier speculated probes were occupied
+                        if (byte[s] & (1u << bitidx[s])) { step = s + 1; t = (s + 1 < kMarchMaxStagedSteps) ? tq[s + 1 < kMarchMaxStagedSteps ? s + 1 : s] : tcur; }
+                        else run = false;
                     }
                 }
+                if (step) { last_t = t; px += 3 * step; pd += 3 * step; pl += 2 * step; }
                 while (t < far && step < nc) {
                     if (probe(r, p, t, x, y, z, dt)) {
                         px[0] = x; px[1] = y; px[2] = z;
@@ -808,6 +809,8 @@ __global__ void __launch_bounds__(kMarchThreads, 6) march_rays_staged_kernel(
                 px += 3; pd += 3; pl += 2;
             }
         }
+        __shared__ uint8_t s_rows[kMarchThreads];                // rows of this chunk somebody will read: filled (+1 for the sentinel)
+        s_rows[threadIdx.x] = (uint8_t)min(filled + 1u, nc);
         if (live_rows) {
             // Row list for the field kernel: the rows this block filled, in ray order; blocks append in arrival order (the list is
             // consumed 128 rows at a time, so locality between consecutive samples of a ray and neighbouring rays is preserved).
@@ -828,15 +831,17 @@ __global__ void __launch_bounds__(kMarchThreads, 6) march_rays_staged_kernel(
             block_copy_out(dirs + row0 * 3, sd, rays_here * n_step * 3);
             block_copy_out(deltas + row0 * 2, sl, rays_here * n_step * 2);
         } else {
-            // one segment of nc rows per ray, n_step rows apart
-            for (uint32_t i = threadIdx.x; i < rays_here * nc * 3; i += kMarchThreads) {
-                const uint32_t ray = i / (nc * 3), o = i - ray * (nc * 3);
-                const size_t dst = ((size_t)(first + ray) * n_step + c0) * 3 + o;
-                xyzs[dst] = sx[i]; dirs[dst] = sd[i];
-            }
-            for (uint32_t i = threadIdx.x; i < rays_here * nc * 2; i += kMarchThreads) {
-                const uint32_t ray = i / (nc * 2), o = i - ray * (nc * 2);
-                deltas[((size_t)(first + ray) * n_step + c0) * 2 + o] = sl[i];
+            // one segment of nc rows per ray, n_step rows apart: a warp writes one ray's segments (<= 96 contiguous bytes each)
+            // per round (an index/division-based mapping of this copy was 37 % of the kernel's instructions)
+            // In a device-driven frame nothing reads past a ray's first sentinel (the field kernel runs over the live-row list,
+            // composite_rays stops at the sentinel): those rows are not written at all — at 64 samples per ray and iteration the
+            // zero fill was a quarter of the marcher's HBM writes.
+            const uint32_t lane = threadIdx.x & 31u;
+            for (uint32_t ray = threadIdx.x >> 5; ray < rays_here; ray += kMarchThreads / 32) {
+                const size_t row = (size_t)(first + ray) * n_step + c0;
+                const uint32_t keep = live_rows ? s_rows[ray] : nc;
+                if (lane < keep * 3) { xyzs[row * 3 + lane] = sx[ray * nc * 3 + lane]; dirs[row * 3 + lane] = sd[ray * nc * 3 + lane]; }
+                if (lane < keep * 2) deltas[row * 2 + lane] = sl[ray * nc * 2 + lane];
             }
         }
         __syncthreads();
