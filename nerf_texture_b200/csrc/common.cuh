@@ -73,6 +73,10 @@ int launch_ngp_field(const float* xyz, const float* dirs, const float* deltas, u
                      const int* offsets, uint32_t L, float S, uint32_t H, int align_corners, const void* w_sigma_f16, const void* w_color_f16,
                      float density_scale, float* sigmas, float* rgbs, cudaStream_t stream);
 
+// per-device caches of launch configuration (one process may drive several GPUs)
+constexpr int kMaxDevices = 64;
+inline int current_device() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < kMaxDevices) ? d : 0; }
+
 inline int device_sm_count() {
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);

@@ -395,8 +395,10 @@ int ntx::launch_ngp_field(const float* xyz, const float* dirs, const float* delt
     if (M == 0) return NTX_OK;
     const uint32_t ns = 2, nc = 3;  // FFMLP(num_layers=2) and FFMLP(num_layers=3): nerf/network_ff.py:31-49
     const FieldPlan plan = field_plan(L, ns, nc);
-    static int occ = 0;
-    static uint32_t configured = 0;
+    static int occ_dev[kMaxDevices] = {};
+    static uint32_t configured_dev[kMaxDevices] = {};
+    int& occ = occ_dev[current_device()];
+    uint32_t& configured = configured_dev[current_device()];
     if (plan.total > configured) {
         if (cudaFuncSetAttribute(ngp_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess) {
             cudaGetLastError();

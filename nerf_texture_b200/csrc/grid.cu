@@ -313,7 +313,8 @@ static int launch_fwd_generic(const float* inputs, const scalar_t* emb, const in
 template <typename scalar_t>
 static int launch_fwd_pair(const float* inputs, const scalar_t* emb, const int* offsets, scalar_t* out, uint32_t B, uint32_t L, float S,
                            uint32_t H, uint32_t gridtype, bool align, int layout, cudaStream_t st) {
-    static int grid_cap = 0;
+    static int grid_cap_dev[kMaxDevices] = {};
+    int& grid_cap = grid_cap_dev[current_device()];
     if (!grid_cap) {
         grid_cap = persistent_grid((const void*)grid_fwd_pair_kernel<scalar_t>, kPairThreads, 0);
         if (tunables().pair_ctas > 0) grid_cap = tunables().pair_ctas * device_sm_count();

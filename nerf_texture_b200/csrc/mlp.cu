@@ -160,8 +160,9 @@ static int launch_mlp(const __half* in, const __half* w, __half* out, __half* fw
                 "FullyFusedMLP: %u bytes of shared memory needed (hidden=%d, input_dim=%u, num_layers=%u) exceed the 227 KB of a B200 SM", plan.total,
                 WIDTH, in_dim, num_layers);
     auto kern = mlp_fused_kernel<WIDTH, TRAIN>;
-    static int configured_smem = -1;
-    static int occ = 1;
+    static int configured_dev[kMaxDevices] = {};
+    int& configured_smem = configured_dev[current_device()];
+    int occ = 1;
     if ((int)plan.total > configured_smem) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess) {
             cudaGetLastError();

@@ -252,7 +252,8 @@ static int launch_dgrad(const __half* grad, const __half* w, const __half* fwd, 
     const BwdPlan plan = bwd_plan(in_dim, WIDTH, num_layers, gi != nullptr);
     NTX_REQUIRE(plan.total <= 227u * 1024u, NTX_ERR_UNSUPPORTED, "FullyFusedMLP backward: %u bytes of shared memory needed exceed the 227 KB of a B200 SM", plan.total);
     auto kern = mlp_dgrad_kernel<WIDTH>;
-    static int configured = -1;
+    static int configured_dev[kMaxDevices] = {};
+    int& configured = configured_dev[current_device()];
     if ((int)plan.total > configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess) {
             cudaGetLastError();

@@ -1162,10 +1162,12 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
     NTX_REQUIRE(max_n_step <= 1024 && (uint64_t)max(N, sample_budget) + 128 < (1ull << 31), NTX_ERR_INVALID_ARGUMENT, "render_rays: bad sample_budget / max_n_step");
     cudaStream_t st = ST(stream);
     const FrameWorkspace w = carve_frame_workspace(workspace, N, sample_budget);
-    // events that bound how far the launching thread runs ahead of the device (one set per process; the call is not re-entrant)
+    // events that bound how far the launching thread runs ahead of the device (one set per device; the call is not re-entrant)
     constexpr int kEvents = 4;
-    static cudaEvent_t ev[kEvents];
-    static bool ev_ready = false;
+    static cudaEvent_t ev_dev[kMaxDevices][kEvents];
+    static bool ev_ready_dev[kMaxDevices] = {};
+    cudaEvent_t* ev = ev_dev[current_device()];
+    bool& ev_ready = ev_ready_dev[current_device()];
     if (!ev_ready) {
         for (int i = 0; i < kEvents; i++)
             if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); set_error("render_rays: cannot create events"); return NTX_ERR_CUDA; }
@@ -1177,7 +1179,8 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
     cudaMemsetAsync(depth, 0, sizeof(float) * N, st);
     cudaMemsetAsync(image, 0, sizeof(float) * 3 * N, st);
     near_far_kernel<<<ceil_div<uint32_t>(N, 128), 128, 0, st>>>(rays_o, rays_d, aabb, N, min_near, w.nears, w.fars);
-    static bool smem_ready = false;
+    static bool smem_ready_dev[kMaxDevices] = {};
+    bool& smem_ready = smem_ready_dev[current_device()];
     const size_t march_smem = (size_t)kMarchThreads * kMarchMaxStagedSteps * 8 * sizeof(float);
     if (!smem_ready) {
         cudaFuncSetAttribute(march_rays_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march_smem);
