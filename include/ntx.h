@@ -180,7 +180,7 @@ int ntx_ngp_field_forward(const float* xyz, const float* dirs, const float* delt
  *   rays_o, rays_d [N,3] f32; aabb [6] f32 (device); grid = density bit-field; occupancy_mip nullable (ntx_build_occupancy_mip)
  *   weights_sum [N], depth [N], image [N,3] f32: overwritten (image WITHOUT the background term, like composite_rays)
  *   workspace: ntx_render_rays_workspace_bytes(N, sample_budget) bytes of device memory, 256-byte aligned
- *   host_mailbox: max_steps + 1 ints of pinned, device-mapped host memory (cudaHostAlloc / torch pin_memory)
+ *   host_mailbox: max_steps + 2*H*C + 8 ints of pinned, device-mapped host memory (cudaHostAlloc / torch pin_memory)
  *   sample_counter: nullable device counter, incremented by the number of samples marched (statistics)
  *   stats_out: nullable host pointer to 2 uint32: [0] loop iterations that had rays alive, [1] kernels launched by this call
  * Not re-entrant (uses one set of events per process). */

@@ -1151,7 +1151,7 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
                                void* workspace, int* host_mailbox, unsigned long long* sample_counter, uint32_t* stats_out, ntx_stream_t stream) {
     NTX_REQUIRE(rays_o && rays_d && aabb && grid && weights_sum && depth && image, NTX_ERR_INVALID_ARGUMENT, "render_rays: null pointer");
     NTX_REQUIRE(workspace, NTX_ERR_WORKSPACE, "render_rays: workspace of ntx_render_rays_workspace_bytes(N) bytes required");
-    NTX_REQUIRE(host_mailbox, NTX_ERR_INVALID_ARGUMENT, "render_rays: host_mailbox must point to max_steps + 1 ints of pinned (mapped) host memory");
+    NTX_REQUIRE(host_mailbox, NTX_ERR_INVALID_ARGUMENT, "render_rays: host_mailbox must point to max_steps + 2*H*C + 8 ints of pinned (mapped) host memory");
     NTX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, NTX_ERR_INVALID_ARGUMENT, "render_rays: workspace must be 256-byte aligned");
     NTX_REQUIRE(C >= 1 && C <= 16 && H >= 1 && H <= 1024 && max_steps >= 1, NTX_ERR_INVALID_ARGUMENT, "render_rays: bad C/H/max_steps");
     if (occupancy_mip && ((H & (H - 1)) != 0 || H < 16)) occupancy_mip = nullptr;
@@ -1186,15 +1186,20 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
         cudaFuncSetAttribute(march_rays_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march_smem);
         smem_ready = true;
     }
+    // Loop bounds.  Without pauses every iteration gives each living ray n_step samples, and `step` (their sum) reaching max_steps
+    // ends the loop like the reference's `while step < max_steps`.  A paused ray spends iterations without sampling — at most
+    // (voxels on a ray) / walk_budget < 2*H*C / walk_budget of them — so the bounds grow by that much; rays still end at t >= far.
+    const uint32_t pause_iters = walk_budget ? 2u * H * C / walk_budget + 2u : 0u;
+    const uint32_t step_limit = max_steps + pause_iters * max_n_step, iter_limit = max_steps + pause_iters;
     uint32_t bound_rays = N, iterations = 0, kernels = 1;   // near_far
-    for (uint32_t i = 0; i < max_steps; i++) {
+    for (uint32_t i = 0; i < iter_limit; i++) {
         const int cur = i & 1, old = cur ^ 1;
         FrameState* s_cur = w.state + cur;
         if (i == 0) {
             frame_init_kernel<<<ceil_div<uint32_t>(N, 256), 256, 0, st>>>(N, sample_budget, max_n_step, w.nears, w.rays_alive[0], w.rays_t[0], s_cur, host_mailbox);
         } else {
             compact_rays_kernel<<<ceil_div<uint32_t>(bound_rays, kCompactThreads * kCompactItems), kCompactThreads, 0, st>>>(
-                bound_rays, w.rays_alive[cur], w.rays_alive[old], w.rays_t[cur], w.rays_t[old], nullptr, w.scan, w.state + old, s_cur, sample_budget, max_n_step, max_steps,
+                bound_rays, w.rays_alive[cur], w.rays_alive[old], w.rays_t[cur], w.rays_t[old], nullptr, w.scan, w.state + old, s_cur, sample_budget, max_n_step, step_limit,
                 host_mailbox + i);
         }
         // padding rows (at most 128) are cleared by the first threads of the launch: at least one block

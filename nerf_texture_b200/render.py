@@ -95,14 +95,14 @@ def auto_schedule(N):
     return (8, 64)
 
 
-def _frame_buffers(dev, N, max_steps, budget):
+def _frame_buffers(dev, N, max_steps, budget, mailbox_len):
     """device workspace + pinned host mailbox of ntx_render_rays, cached per (device, stream, N, budget)"""
-    key = (dev.index, L.stream(), N, max_steps, budget)
+    key = (dev.index, L.stream(), N, mailbox_len, budget)
     buf = _frame_cache.get(key)
     if buf is None:
         ws = torch.empty(L.lib().ntx_render_rays_workspace_bytes(N, budget) + 256, dtype=torch.uint8, device=dev)
         off = (-ws.data_ptr()) % 256
-        mailbox = torch.zeros(max_steps + 1, dtype=torch.int32).pin_memory()
+        mailbox = torch.zeros(mailbox_len, dtype=torch.int32).pin_memory()
         counter = torch.zeros(1, dtype=torch.int64, device=dev)
         buf = (ws, ws.data_ptr() + off, mailbox, counter)
         _frame_cache.clear()          # one frame size at a time is the normal case; do not hoard workspaces
@@ -148,7 +148,7 @@ def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aab
             schedule = "reference" if perturb else auto_schedule(N)
         mult, cap = SCHEDULES[schedule] if isinstance(schedule, str) else schedule
         budget = int(mult) * N
-        ws, ws_ptr, mailbox, counter = _frame_buffers(dev, N, int(max_steps), budget)
+        ws, ws_ptr, mailbox, counter = _frame_buffers(dev, N, int(max_steps), budget, int(max_steps) + 2 * int(grid_size) * int(cascade) + 8)
         image_c = torch.empty(N, 3, dtype=torch.float32, device=dev)
         depth_c = torch.empty(N, dtype=torch.float32, device=dev)
         wsum_c = torch.empty(N, dtype=torch.float32, device=dev)

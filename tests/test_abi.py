@@ -57,3 +57,19 @@ def test_product_never_touches_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|libntx_oracle|#include.*oracle|dlopen", txt, flags=re.M):
                     bad.append(os.path.join(base, f))
     assert not bad, bad
+
+
+def test_binding_arity_matches_the_header():
+    """every ctypes signature in _lib.py has exactly as many arguments as the declaration in include/ntx.h"""
+    from nerf_texture_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "ntx.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decl = {}
+    for m in re.finditer(r"\b(ntx_[a-z0-9_A-Z]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        decl[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    sigs = dict(_lib._SIGS)
+    sigs.update(_lib._SIZE_FNS)
+    wrong = {n: (len(a), decl[n]) for n, a in sigs.items() if n in decl and len(a) != decl[n]}
+    assert not wrong, wrong
+    assert set(sigs) <= set(decl), sorted(set(sigs) - set(decl))

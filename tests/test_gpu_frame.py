@@ -87,3 +87,35 @@ def test_render_rays_rejects_missing_workspace_and_mailbox():
     ws = torch.zeros(1 << 16, dtype=torch.uint8, device=DEV)
     with pytest.raises(RuntimeError, match="mailbox"):
         L.call("ntx_render_rays", *args, ws.data_ptr() + (-ws.data_ptr()) % 256, None, None, ctypes.addressof(it), L.stream())
+
+
+def test_paused_rays_cross_a_long_gap_between_two_objects():
+    """Two small balls on the camera axis, 1.3 units (83 voxels) apart: after the first ball every ray walks a long empty stretch.
+    With a walk budget the marcher pauses such rays several iterations in a row; they must still reach the second ball with the
+    reference's samples, and the loop must not run out of its step budget on the way (max_steps kept small on purpose)."""
+    L = ntx()
+    import math
+    from _util import ball_density_grid
+    from nerf_texture_b200 import render, scene
+    field = render.NGPField.random(torch.device(DEV), seed=5)
+    rays_o, rays_d = scene.pinhole_rays(48, 48, DEV, fovy_deg=20.0)
+    az, el = math.radians(30.0), math.radians(20.0)
+    fwd = -np.array([math.cos(el) * math.sin(az), math.sin(el), math.cos(el) * math.cos(az)])
+    grid = np.maximum(ball_density_grid(1, 128, 1.0, 0.12, tuple(-0.65 * fwd)), ball_density_grid(1, 128, 1.0, 0.12, tuple(0.65 * fwd)))
+    dens = torch.from_numpy(grid.reshape(-1)).to(DEV)
+    bits = torch.zeros(128 ** 3 // 8, dtype=torch.uint8, device=DEV)
+    L.call("ntx_packbits", dens.data_ptr(), dens.numel() // 8, 0.5, bits.data_ptr(), L.stream())   # N counts bit-field bytes (raymarching.py:204)
+    ref = render.render_rays(field, rays_o, rays_d, bits, 1, 128, count_samples=True, schedule="reference", max_steps=256)
+    assert ref["n_samples"] > 0
+    for sched in [(1, 8), "auto", (2, 3)]:
+        for wb in (4, 16):
+            render.WALK_BUDGET, old = wb, render.WALK_BUDGET
+            try:
+                out = render.render_rays(field, rays_o, rays_d, bits, 1, 128, count_samples=True, schedule=sched, max_steps=256)
+            finally:
+                render.WALK_BUDGET = old
+            assert out["n_samples"] == ref["n_samples"], (sched, wb)
+            for k in ("image", "depth", "weights_sum"):
+                np.testing.assert_array_equal(out[k].cpu().numpy(), ref[k].cpu().numpy(), err_msg="%s %s %d" % (k, sched, wb))
+    # both balls are really seen: some rays accumulate samples from two separate stretches
+    assert float(ref["weights_sum"].max()) > 0

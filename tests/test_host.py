@@ -110,3 +110,14 @@ def test_two_rank_gather_frame_gloo(tmp_path):
     outs = [p.communicate(timeout=120) for p in procs]
     for r, (so, se) in enumerate(outs):
         assert "RANK%d OK" % r in so, (so, se[-2000:])
+
+
+def test_sample_schedules():
+    """schedule helpers of the device-driven frame (render.py): the reference's rule is (N, 8); auto never asks for fewer samples
+    per iteration than the reference and stays within the marcher's chunking"""
+    from nerf_texture_b200 import render
+    assert render.SCHEDULES["reference"] == (1, 8)
+    for n in (1, 100, 1 << 17, 1 << 20, 1 << 22):
+        mult, cap = render.auto_schedule(n)
+        assert mult >= 1 and 8 <= cap <= 1024
+    assert render.WALK_BUDGET > 0
