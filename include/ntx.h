@@ -183,7 +183,10 @@ int ntx_ngp_field_forward(const float* xyz, const float* dirs, const float* delt
  *   host_mailbox: max_steps + 2*H*C + 8 ints of pinned, device-mapped host memory (cudaHostAlloc / torch pin_memory)
  *   sample_counter: nullable device counter, incremented by the number of samples marched (statistics)
  *   stats_out: nullable host pointer to 2 uint32: [0] loop iterations that had rays alive, [1] kernels launched by this call
- * Not re-entrant (uses one set of events per process). */
+ *   kernel_ms_out: nullable host pointer to 2 floats.  When given, every march and field launch of the frame is bracketed by
+ *     CUDA events on `stream`, the call synchronises the stream at the end and returns [0] the summed march-kernel time and
+ *     [1] the summed field-kernel time in ms (bench.py's roofline; costs a few event records, do not use in production).
+ * Not re-entrant (uses one set of events per device). */
 size_t ntx_render_rays_workspace_bytes(uint32_t N, uint32_t sample_budget);
 int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const float* aabb, float min_near, float bound,
                     float dt_gamma, uint32_t max_steps, uint32_t perturb, uint32_t sample_budget, uint32_t max_n_step,
@@ -191,7 +194,8 @@ int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const 
                     const uint8_t* occupancy_mip, const void* embeddings_f16, const int* offsets, uint32_t L, float S,
                     uint32_t base_resolution, int align_corners, const void* w_sigma_f16, const void* w_color_f16,
                     float density_scale, float* weights_sum, float* depth, float* image, void* workspace,
-                    int* host_mailbox, unsigned long long* sample_counter, uint32_t* stats_out, ntx_stream_t stream);
+                    int* host_mailbox, unsigned long long* sample_counter, uint32_t* stats_out, float* kernel_ms_out,
+                    ntx_stream_t stream);
 
 #ifdef __cplusplus
 }

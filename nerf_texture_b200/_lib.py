@@ -43,7 +43,7 @@ _SIGS = {
     "ntx_compact_rays": [_u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ntx_ngp_field_forward": [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _u32, _f32, _u32, _int, _vp, _vp, _f32, _vp, _vp, _vp],
     "ntx_render_rays": [_vp, _vp, _u32, _vp, _f32, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _u32, _f32, _u32, _int, _vp, _vp, _f32,
-                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
 }
 _SIZE_FNS = {
     "ntx_march_rays_train_workspace_bytes": [_u32],

@@ -1165,7 +1165,8 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
                                const uint8_t* occupancy_mip,
                                const void* embeddings_f16, const int* offsets, uint32_t L, float S, uint32_t base_resolution, int align_corners,
                                const void* w_sigma_f16, const void* w_color_f16, float density_scale, float* weights_sum, float* depth, float* image,
-                               void* workspace, int* host_mailbox, unsigned long long* sample_counter, uint32_t* stats_out, ntx_stream_t stream) {
+                               void* workspace, int* host_mailbox, unsigned long long* sample_counter, uint32_t* stats_out, float* kernel_ms_out,
+                               ntx_stream_t stream) {
     NTX_REQUIRE(rays_o && rays_d && aabb && grid && weights_sum && depth && image, NTX_ERR_INVALID_ARGUMENT, "render_rays: null pointer");
     NTX_REQUIRE(workspace, NTX_ERR_WORKSPACE, "render_rays: workspace of ntx_render_rays_workspace_bytes(N) bytes required");
     NTX_REQUIRE(host_mailbox, NTX_ERR_INVALID_ARGUMENT, "render_rays: host_mailbox must point to max_steps + 2*H*C + 8 ints of pinned (mapped) host memory");
@@ -1209,6 +1210,20 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
     const uint32_t pause_iters = walk_budget ? 2u * H * C / walk_budget + 2u : 0u;
     const uint32_t step_limit = max_steps + pause_iters * max_n_step, iter_limit = max_steps + pause_iters;
     uint32_t bound_rays = N, iterations = 0, kernels = 1;   // near_far
+    // optional per-kernel timing (bench.py's roofline): CUDA events around every march and field launch of this frame
+    constexpr uint32_t kProfIters = 256;
+    static cudaEvent_t* prof_dev[kMaxDevices] = {};
+    cudaEvent_t* prof = nullptr;
+    uint32_t prof_iters = 0;
+    if (kernel_ms_out) {
+        kernel_ms_out[0] = kernel_ms_out[1] = 0.f;
+        cudaEvent_t*& pool = prof_dev[current_device()];
+        if (!pool) {
+            pool = new cudaEvent_t[3 * kProfIters];
+            for (uint32_t e = 0; e < 3 * kProfIters; e++) cudaEventCreate(&pool[e]);
+        }
+        prof = pool;
+    }
     for (uint32_t i = 0; i < iter_limit; i++) {
         const int cur = i & 1, old = cur ^ 1;
         FrameState* s_cur = w.state + cur;
@@ -1219,15 +1234,19 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
                 bound_rays, w.rays_alive[cur], w.rays_alive[old], w.rays_t[cur], w.rays_t[old], nullptr, w.scan, w.state + old, s_cur, sample_budget, max_n_step, step_limit,
                 host_mailbox + i);
         }
+        const bool timed = prof && i < kProfIters;
+        if (timed) { cudaEventRecord(prof[3 * i], st); prof_iters = i + 1; }
         // padding rows (at most 128) are cleared by the first threads of the launch: at least one block
         march_rays_staged_kernel<<<ceil_div<uint32_t>(max(bound_rays, 128u), kMarchThreads), kMarchThreads, march_smem, st>>>(
             bound_rays, 1, w.rays_alive[cur], w.rays_t[cur], rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, w.nears, w.fars, w.xyzs, w.dirs, w.deltas, perturb, 0,
             occupancy_mip, s_cur, sample_counter, walk_budget, w.live_rows, &s_cur->n_live);
         const uint32_t m_bound = (uint32_t)min((uint64_t)max(N, sample_budget), (uint64_t)bound_rays * max_n_step) + 128u;
+        if (timed) cudaEventRecord(prof[3 * i + 1], st);
         // the field runs over the list of rows the marcher filled (no tile is spent on sentinel rows)
         const int rc = launch_ngp_field(w.xyzs, w.dirs, nullptr, m_bound, &s_cur->n_live, w.live_rows, bound, embeddings_f16, offsets, L, S, base_resolution,
                                         align_corners, w_sigma_f16, w_color_f16, density_scale, w.sigmas, w.rgbs, st);
         if (rc != NTX_OK) return rc;
+        if (timed) cudaEventRecord(prof[3 * i + 2], st);
         composite_rays_kernel<<<ceil_div<uint32_t>(bound_rays, 128), 128, 0, st>>>(bound_rays, 1, w.rays_alive[cur], w.rays_t[cur], w.sigmas, w.rgbs, w.deltas, weights_sum,
                                                                                   depth, image, s_cur);
         kernels += 4;                                       // init | compact, march, field, composite
@@ -1243,5 +1262,14 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
         }
     }
     if (stats_out) { stats_out[0] = iterations; stats_out[1] = kernels; }
+    if (prof && prof_iters) {
+        if (cudaStreamSynchronize(st) != cudaSuccess) return check_launch("render_rays");
+        for (uint32_t i = 0; i < prof_iters; i++) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, prof[3 * i], prof[3 * i + 1]);
+            cudaEventElapsedTime(&b, prof[3 * i + 1], prof[3 * i + 2]);
+            kernel_ms_out[0] += a; kernel_ms_out[1] += b;
+        }
+    }
     return check_launch("render_rays");
 }

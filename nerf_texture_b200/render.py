@@ -118,13 +118,14 @@ def _aabb_tensor(bound, dev, cache={}):
 
 
 def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aabb=None, min_near=0.2, dt_gamma=0.0, max_steps=1024, bg_color=1.0,
-                perturb=0, count_samples=False, profile=None, use_mip=True, device_loop=True, mip=None, schedule="auto"):
+                perturb=0, count_samples=False, profile=None, use_mip=True, device_loop=True, mip=None, schedule="auto", time_kernels=False):
     """Inference branch of NeRFRenderer.run_cuda (renderer.py:436-489).  rays_o/d [N,3] fp32 CUDA.
     Returns dict(image [N,3], depth [N], weights_sum [N], iterations, n_samples (if count_samples)).
     device_loop=True (default): the whole loop is ONE libntx call whose iteration state stays on the device (ntx_render_rays);
     device_loop=False: the reference's structure, one extension call per step and a blocking n_alive read per iteration
     (bit-identical results; kept for profiling and as the parity reference of the device-driven loop).
     profile: optional list (stepwise loop only); gets one (start_event, stop_event, live_sample_count_tensor) per field-kernel launch.
+    time_kernels (device loop only): also return march_ms / field_ms, the summed CUDA-event times of the frame's march and field launches.
     mip: optional pre-built occupancy mip (ntx_build_occupancy_mip) of density_bitfield.
     schedule (device loop only): "auto" (auto_schedule(N); the reference's when perturb != 0), "reference", "wide", or a
     (budget_multiple, max_n_step) pair — the image is the same either way, see include/ntx.h."""
@@ -155,16 +156,19 @@ def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aab
         if count_samples:
             counter.zero_()
         stats = (ctypes.c_uint32 * 2)()
+        kms = (ctypes.c_float * 2)()
         L.call("ntx_render_rays", L.ptr(rays_o), L.ptr(rays_d), N, L.ptr(aabb), float(min_near), float(bound), float(dt_gamma), int(max_steps), int(perturb),
                budget, int(cap), walk, int(cascade), int(grid_size), L.ptr(density_bitfield), None if mip is None else L.ptr(mip), L.ptr(field.table), L.ptr(field.offsets),
                field.num_levels, field.S, field.H, int(field.align_corners), L.ptr(field.w_sigma), L.ptr(field.w_color), float(field.density_scale),
                L.ptr(wsum_c), L.ptr(depth_c), L.ptr(image_c), ws_ptr, mailbox.data_ptr(), counter.data_ptr() if count_samples else None,
-               ctypes.addressof(stats), st)
+               ctypes.addressof(stats), ctypes.addressof(kms) if time_kernels else None, st)
         L.launches += int(stats[1]) - 1          # L.call counted the call as one launch
         image = image_c + (1 - wsum_c).unsqueeze(-1) * bg_color
         out = dict(image=image, depth=depth_c, weights_sum=wsum_c, iterations=int(stats[0]))
         if count_samples:
             out["n_samples"] = int(counter.item())
+        if time_kernels:
+            out["march_ms"], out["field_ms"] = float(kms[0]), float(kms[1])
         return out
     nears = torch.empty(N, dtype=torch.float32, device=dev)
     fars = torch.empty(N, dtype=torch.float32, device=dev)

@@ -83,10 +83,10 @@ def test_render_rays_rejects_missing_workspace_and_mailbox():
     args = [d.data_ptr(), d.data_ptr(), 1, d.data_ptr(), 0.2, 1.0, 0.0, 8, 0, 0, 0, 0, 1, 128, d.data_ptr(), None, d.data_ptr(), d.data_ptr(), 16, 0.5, 16, 1, d.data_ptr(),
             d.data_ptr(), 1.0, d.data_ptr(), d.data_ptr(), d.data_ptr()]
     with pytest.raises(RuntimeError, match="workspace"):
-        L.call("ntx_render_rays", *args, None, None, None, ctypes.addressof(it), L.stream())
+        L.call("ntx_render_rays", *args, None, None, None, ctypes.addressof(it), None, L.stream())
     ws = torch.zeros(1 << 16, dtype=torch.uint8, device=DEV)
     with pytest.raises(RuntimeError, match="mailbox"):
-        L.call("ntx_render_rays", *args, ws.data_ptr() + (-ws.data_ptr()) % 256, None, None, ctypes.addressof(it), L.stream())
+        L.call("ntx_render_rays", *args, ws.data_ptr() + (-ws.data_ptr()) % 256, None, None, ctypes.addressof(it), None, L.stream())
 
 
 def test_paused_rays_cross_a_long_gap_between_two_objects():
