@@ -268,7 +268,9 @@ def main():
         achieved = live * FIELD_BYTES_PER_SAMPLE / kt / 1e9
         traffic = None   # DRAM bytes of one in-frame launch from the committed `ncu --set full` capture (profiles/)
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_field_kernel_traffic.json")))["dram_bytes_per_launch_in_frame"]
+            # the capture is of ONE (large) launch; scale its DRAM-bytes-per-algorithmic-byte to this run's average launch
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_field_kernel_traffic.json")))
+            traffic = int(tj["dram_bytes_per_algorithmic_byte"] * live * FIELD_BYTES_PER_SAMPLE / max(nlaunch, 1))
         except Exception:
             pass
         line["roofline"] = {"bound": "hbm", "kernel": "ngp_field_kernel (hash-grid gather + sigma MLP + SH + colour MLP)", "achieved": achieved,
