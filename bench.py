@@ -51,6 +51,29 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        # NVML from a thread (a sample every ~5 ms: a timed region of ten 8 ms frames gets ~16 of them); nvidia-smi -lms as fallback
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.samples, self.mask, self.running = [], 0, True
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while self.running:
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
+                        self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -64,6 +87,12 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if getattr(self, "nvml", None) is not None:
+            self.running = False
+            self.thread.join(timeout=1)
+            bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(n for n, b in bits.items() if self.mask & b), "samples": len(self.samples), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
