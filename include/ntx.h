@@ -140,6 +140,10 @@ int ntx_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, con
  * mip: ntx_occupancy_mip_bytes(C,H) bytes; rebuild whenever the bit-field changes.  H must be a power of two >= 16. */
 size_t ntx_occupancy_mip_bytes(uint32_t C, uint32_t H);
 int ntx_build_occupancy_mip(const uint8_t* grid, uint32_t C, uint32_t H, uint8_t* mip, ntx_stream_t stream);
+/* composite_rays (raymarching.cu:1021-1104).  One extension over the reference: a slot with deltas == (0, -t), t > 0, is the
+ * "paused" marker the marcher of ntx_render_rays writes (walk_budget): the ray stops compositing there but stays alive with
+ * rays_t = t.  The reference's marcher (and ntx_march_rays) only ever writes (0, 0) into unused slots, for which the behaviour
+ * is the reference's: rays_t = -1. */
 int ntx_composite_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, float* rays_t, const float* sigmas,
                        const float* rgbs, const float* deltas, float* weights_sum, float* depth, float* image,
                        ntx_stream_t stream);
