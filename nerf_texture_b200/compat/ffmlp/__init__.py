@@ -1,1 +1,2 @@
-from .ffmlp import FFMLP, ffmlp_forward, convert_activation
+"""`ffmlp` drop-in package (libntx): fully-fused fp16 MLP on tcgen05."""
+from nerf_texture_b200.operators import FFMLP, convert_activation, ffmlp_forward  # noqa: F401
