@@ -121,3 +121,20 @@ def test_sample_schedules():
         mult, cap = render.auto_schedule(n)
         assert mult >= 1 and 8 <= cap <= 1024
     assert render.WALK_BUDGET > 0
+
+
+def test_level_offsets_match_the_oracle_and_the_reference_rule():
+    """operators.hashgrid_level_offsets (what GridEncoder allocates) == the oracle's table sizing for every encoder config the
+    reference builds (gridencoder/grid.py:113-124: min(2^T, R^D) entries per level, rounded up to a multiple of 8)"""
+    import numpy as np
+    from _util import cfgA, cfgB, cfgT, oracle
+    from nerf_texture_b200.operators import GridEncoder, hashgrid_level_offsets
+    O = oracle()
+    for cfg in (cfgA(), cfgB(), cfgT(), dict(input_dim=2, num_levels=6, level_dim=4, per_level_scale=1.5, base_resolution=8, log2_hashmap_size=10, align_corners=False)):
+        want, pls = O.grid_offsets(**{k: v for k, v in cfg.items() if k != "level_dim"})
+        enc = GridEncoder(**cfg)
+        assert enc.offsets.dtype == torch.int32 and enc.offsets.tolist() == [int(v) for v in want]
+        assert abs(float(enc.per_level_scale) - float(pls)) < 1e-12
+        got = hashgrid_level_offsets(cfg["input_dim"], cfg["num_levels"], enc.per_level_scale, cfg["base_resolution"], cfg["log2_hashmap_size"], cfg["align_corners"])
+        assert got == enc.offsets.tolist() and all(n % 8 == 0 for n in np.diff(got))
+        assert enc.embeddings.shape == (got[-1], cfg["level_dim"]) and enc.output_dim == cfg["num_levels"] * cfg["level_dim"]
