@@ -14,8 +14,11 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-OBJDIR = os.path.join(LIBDIR, "obj")
-LIB = os.path.join(LIBDIR, "libntx.so")
+# development variants: NTX_BUILD_TAG=probe NTX_NVCC_EXTRA=-DNTX_DEV_PROBES builds lib/libntx_probe.so next to the product library
+# (select it at run time with NTX_LIB_PATH); the product build has no tag
+_TAG = os.environ.get("NTX_BUILD_TAG", "")
+OBJDIR = os.path.join(LIBDIR, "obj" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(LIBDIR, "libntx" + ("_" + _TAG if _TAG else "") + ".so")
 SOURCES = ["api.cu", "grid.cu", "sh.cu", "raymarch.cu", "mlp.cu", "mlp_bwd.cu", "field.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -18,9 +18,32 @@ const Tunables& tunables() {
         const char* e;
         v.field_ctas = (e = getenv("NTX_FIELD_CTAS")) ? atoi(e) : 0;
         v.pair_ctas = (e = getenv("NTX_PAIR_CTAS")) ? atoi(e) : 0;
+        v.mlp_impl = (e = getenv("NTX_MLP_IMPL")) ? atoi(e) : 0;
         return v;
     }();
     return t;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: libntx links only the (static) runtime, libcuda is the
+// process's own.  2-D row-major fp16 tensor [rows x inner]; a box is `box_rows` rows of `box_inner` elements.
+int make_tensor_map_2d_f16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows) {
+    using encode_fn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); fn = nullptr; }
+        return reinterpret_cast<encode_fn>(fn);
+    }();
+    if (!encode) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return NTX_ERR_CUDA; }
+    const cuuint64_t dims[2] = {inner, rows};
+    const cuuint64_t strides[1] = {inner * 2};       // bytes between rows
+    const cuuint32_t box[2] = {box_inner, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for a [%llu x %llu] fp16 tensor", (int)r, (unsigned long long)rows, (unsigned long long)inner); return NTX_ERR_CUDA; }
+    return NTX_OK;
 }
 }  // namespace ntx
 

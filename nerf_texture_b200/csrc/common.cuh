@@ -26,6 +26,7 @@ void set_error(const char* fmt, ...);
 struct Tunables {
     int field_ctas;          // NTX_FIELD_CTAS: resident CTAs per SM of the fused field kernel (0 = as many as fit)
     int pair_ctas;           // NTX_PAIR_CTAS: same for the stand-alone pair gather kernel
+    int mlp_impl;            // NTX_MLP_IMPL: 0 = pipelined kernel (TMA ring, activations in tensor memory), 1 = round-1 kernel (A/B measurements)
 };
 const Tunables& tunables();
 
@@ -72,6 +73,9 @@ inline int resident_ctas_per_sm(const void* func, int threads, size_t dyn_smem, 
 int launch_ngp_field(const float* xyz, const float* dirs, const float* deltas, uint32_t M, const int* M_dev, const int* rows, float bound, const void* embeddings_f16,
                      const int* offsets, uint32_t L, float S, uint32_t H, int align_corners, const void* w_sigma_f16, const void* w_color_f16,
                      float density_scale, float* sigmas, float* rgbs, cudaStream_t stream);
+
+// api.cu: TMA descriptor of a row-major fp16 matrix (driver entry point resolved at run time, no link-time libcuda dependency)
+int make_tensor_map_2d_f16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows);
 
 // per-device caches of launch configuration (one process may drive several GPUs)
 constexpr int kMaxDevices = 64;

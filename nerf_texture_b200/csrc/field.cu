@@ -11,16 +11,14 @@
 //   * 12 producer warps gather features straight into the shared-memory A operand of the first UMMA.  A warp (16 lane
 //     pairs) takes 16-row slices of the CTA's tile sequence round-robin, so the producers run up to kStages tiles ahead;
 //     the feature tile is handed back as soon as the first MMA has read it;
-//   * 4 consumer warps (one per TMEM lane quarter) run the two MLPs: one thread issues the tcgen05.mma of a layer, the
-//     warps pull the accumulator out of TMEM, apply ReLU, round to fp16 and write the next layer's A operand; between the
-//     nets they evaluate SH(dir) and put it next to geo_feat as the colour net's input;
-//   * the MMA -> epilogue chain is 7 dependent stages per tile and each stage is mostly latency (the issuing thread and
-//     the epilogue warps share their schedulers with the producers: measured ~900 cycles per stage of which the MMA is
-//     ~130, tools/field_probe.py).  The consumers therefore keep TWO tiles in flight (two TMEM accumulators, two
-//     activation buffers) and alternate between them stage by stage: while one tile's MMA runs, the other tile's epilogue
-//     does;
-//   * shared memory is kept under 100 KB per CTA on purpose: the gather's throughput follows the L1 capacity left over
-//     by the carve-out (228 KB carve-out: 2x slower, profiles/r01_summary.md).
+//   * 4 consumer warps (one per TMEM lane quarter) run the two MLPs: one elected thread issues the tcgen05.mma of a layer; the
+//     warps pull the fp32 accumulator out of tensor memory (tcgen05.ld), apply ReLU, round to fp16 and write the tile straight
+//     back into tensor memory (tcgen05.st) as the A operand of the next layer's MMA (A-from-TMEM form).  Hidden activations,
+//     geo_feat and the SH basis never exist in shared memory: no STS, no generic->async proxy fence in the layer chain, and the
+//     16 KB activation buffer of round 1 is gone (the gather's throughput follows the L1 capacity the carve-out leaves);
+//   * the MMA -> epilogue chain is 7 dependent stages per tile; one tile per CTA is in flight (two resident CTAs per SM give
+//     the tensor pipe a second chain to interleave with) — ping-pong inside a CTA measured slower in round 1;
+//   * shared memory is kept small on purpose: weights 36 KB + the producer->consumer feature ring.
 // Only xyz/dir (24 B) come in and sigma/rgb (16 B) go out per sample.
 #include "grid_common.cuh"
 #include "mlp_tile.cuh"
@@ -34,7 +32,7 @@ namespace ntx {
 #ifndef NTX_FIELD_STAGES
 #define NTX_FIELD_STAGES 3
 #endif
-constexpr int kConsumerWarps = 4;   // 4: one per TMEM lane quarter | 8: two per quarter, warp w reads lanes 32*(w&3).., columns 32*(w>>2)..
+constexpr int kConsumerWarps = 4;   // one per TMEM lane quarter
 constexpr int kProducerWarps = NTX_FIELD_PRODUCERS;
 constexpr int kTaskRows = 16;                                            // rows one producer warp gathers at a time
 constexpr int kTasksPerTile = 8;                                         // kTileRows / kTaskRows
@@ -43,14 +41,14 @@ constexpr int kFW = 64;          // hidden width of both MLPs
 constexpr int kColorIn = 32;     // SH(16) + geo_feat(15) + zero pad (network_ff.py:42,95-97)
 constexpr int kFieldMaxLevels = 32;
 constexpr int kStages = NTX_FIELD_STAGES;       // feature tiles in the producer -> consumer ring
-constexpr int kCtx = 1;          // tiles the consumers keep in flight (2 = ping-pong; measured slower)
-constexpr uint32_t kFieldTmemCols = 64 * kCtx;
+constexpr uint32_t kOpndCol = 64;      // fp16 A operand [128 x 64] of the next layer: 32 columns behind the accumulator
+constexpr uint32_t kFieldTmemCols = 128;
 
 struct FieldPlan {
     uint32_t k0;                 // sigma-net input width = 2L
     uint32_t ws_bytes, wc_bytes; // weight bytes of the two nets
-    uint32_t ws_off, wc_off, a0_off, h_off, lv_off, misc_off, total;
-    uint32_t a0_stage, h_bytes;
+    uint32_t ws_off, wc_off, a0_off, lv_off, misc_off, total;
+    uint32_t a0_stage;
 };
 __host__ __device__ inline FieldPlan field_plan(uint32_t L, uint32_t ns, uint32_t nc) {
     FieldPlan p;
@@ -60,10 +58,8 @@ __host__ __device__ inline FieldPlan field_plan(uint32_t L, uint32_t ns, uint32_
     p.ws_off = 0;
     p.wc_off = p.ws_off + p.ws_bytes;
     p.a0_stage = kTileRows * p.k0 * 2u;
-    p.h_bytes = kTileRows * kFW * 2u;
     p.a0_off = (p.wc_off + p.wc_bytes + 127u) & ~127u;
-    p.h_off = p.a0_off + kStages * p.a0_stage;
-    p.lv_off = p.h_off + kCtx * p.h_bytes;
+    p.lv_off = p.a0_off + kStages * p.a0_stage;
     p.misc_off = p.lv_off + (uint32_t)sizeof(PairLevel) * kFieldMaxLevels;
     p.total = p.misc_off + 128u;
     return p;
@@ -83,27 +79,17 @@ __device__ unsigned long long g_probe[8];   // consumer: wait_full, wait_mma, ep
 
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kConsumerWarps) : "memory"); }
 
-// hidden-layer epilogue: warp w owns TMEM lanes 32*(w&3).. (= tile rows) and columns 32*(w>>2)..+31: two 16-column passes
-// (the stage chain is latency-bound: splitting a row's 64 columns over two warps halves the dependent instruction chain)
-__device__ __forceinline__ void field_hidden_epilogue(uint32_t tmem_acc, uint8_t* h_smem, uint32_t warp, uint32_t lane) {
-    const uint32_t quarter = warp & 3u, row = quarter * 32 + lane;
+// hidden-layer epilogue: warp q owns TMEM lanes 32q.. (= tile rows): accumulator columns -> ReLU -> fp16 -> operand columns,
+// 32 accumulator columns per pass (the kernel lives in 64 registers per thread)
+__device__ __forceinline__ void field_hidden_epilogue(uint32_t acc, uint32_t opnd) {
 #pragma unroll
-    constexpr int kPasses = 16 / kConsumerWarps;             // 16-column passes per warp
-#pragma unroll
-    for (int q = 0; q < kPasses; q++) {
-        const uint32_t col = (warp >> 2) * (16 * kPasses) + q * 16;
-        uint32_t v[16];
-        tc::tmem_ld_x16(tmem_acc + ((quarter * 32u) << 16) + col, v);
+    for (int h = 0; h < kFW; h += 32) {
+        uint32_t v[32], o[16];
+        tc::tmem_ld_x32(acc + h, v);
         tc::tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; j += 8) {
-            uint4 o;
-            o.x = act_pack2(0, v[j + 0], v[j + 1]);
-            o.y = act_pack2(0, v[j + 2], v[j + 3]);
-            o.z = act_pack2(0, v[j + 4], v[j + 5]);
-            o.w = act_pack2(0, v[j + 6], v[j + 7]);
-            *reinterpret_cast<uint4*>(h_smem + kmajor_chunk_off(row, (col + j) >> 3, kFW)) = o;
-        }
+        for (int j = 0; j < 16; j++) o[j] = act_pack2(0, v[2 * j], v[2 * j + 1]);
+        tc::tmem_st_x16(opnd + (h >> 1), o);
     }
 }
 
@@ -114,16 +100,23 @@ __device__ __forceinline__ void field_hidden_epilogue(uint32_t tmem_acc, uint8_t
 //   st = ns+1       h [128 x 32] . Wc0^T  -> 64      hidden epilogue
 //   st = ns+2..ns+nc                      -> 64      hidden epilogue
 //   st = ns+nc+1    h . Wc_out^T          -> 16      rgb
-__device__ __forceinline__ void field_issue_stage(uint32_t st, uint32_t ns, uint32_t nc, uint32_t K0, uint32_t h_addr, uint32_t ws_addr, uint32_t wc_addr,
+__device__ __forceinline__ void issue_layer_tmem(uint32_t tmem_a, uint32_t w_smem, uint32_t Kdim, uint32_t N, uint32_t tmem_d) {
+    const uint32_t idesc = tc::idesc_f16_f32(kTileRows, N);
+    for (uint32_t ks = 0; ks < (Kdim >> 4); ks++) {
+        const uint64_t db = tc::smem_desc_kmajor_noswz(w_smem + ks * 256u, 128u, Kdim * 16u);
+        tc::mma_f16_ts(tmem_d, tmem_a + ks * 8u, db, idesc, ks > 0 ? 1u : 0u);     // 8 operand columns per K = 16 step
+    }
+}
+__device__ __forceinline__ void field_issue_stage(uint32_t st, uint32_t ns, uint32_t nc, uint32_t K0, uint32_t tmem_a, uint32_t ws_addr, uint32_t wc_addr,
                                                   uint32_t tmem_acc) {
     if (st <= ns) {
         const uint32_t w = ws_addr + kFW * K0 * 2u + (st - 1) * (kFW * kFW * 2u);
-        issue_layer(h_addr, w, kFW, st == ns ? 16u : (uint32_t)kFW, tmem_acc);
+        issue_layer_tmem(tmem_a, w, kFW, st == ns ? 16u : (uint32_t)kFW, tmem_acc);
     } else if (st == ns + 1) {
-        issue_layer(h_addr, wc_addr, kColorIn, kFW, tmem_acc);
+        issue_layer_tmem(tmem_a, wc_addr, kColorIn, kFW, tmem_acc);
     } else {
         const uint32_t w = wc_addr + kFW * kColorIn * 2u + (st - ns - 2) * (kFW * kFW * 2u);
-        issue_layer(h_addr, w, kFW, st == ns + nc + 1 ? 16u : (uint32_t)kFW, tmem_acc);
+        issue_layer_tmem(tmem_a, w, kFW, st == ns + nc + 1 ? 16u : (uint32_t)kFW, tmem_acc);
     }
 }
 
@@ -138,12 +131,11 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
     uint8_t* ws_smem = smem + plan.ws_off;
     uint8_t* wc_smem = smem + plan.wc_off;
     uint8_t* a0_smem = smem + plan.a0_off;   // kStages tiles
-    uint8_t* h_smem = smem + plan.h_off;     // kCtx activation buffers
     PairLevel* lv = reinterpret_cast<PairLevel*>(smem + plan.lv_off);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + plan.misc_off);        // [kStages] producers -> consumer
     uint64_t* empty_bar = full_bar + kStages;                                      // [kStages] consumer (MMA completion) -> producers
-    uint64_t* mma_bar = empty_bar + kStages;                                       // [kCtx] layer done -> consumer warps
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + kCtx);
+    uint64_t* mma_bar = empty_bar + kStages;                                       // layer done -> consumer warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t K0 = plan.k0;
@@ -151,7 +143,7 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
     // ---- one-time setup (all 16 warps) ---------------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) { tc::mbar_init(&full_bar[s], kTasksPerTile); tc::mbar_init(&empty_bar[s], 1); }
-        for (int c = 0; c < kCtx; c++) tc::mbar_init(&mma_bar[c], 1);
+        tc::mbar_init(mma_bar, 1);
         tc::fence_mbar_init();
     }
     if (warp == 0) tc::tmem_alloc<kFieldTmemCols>(tmem_slot);
@@ -223,122 +215,94 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
         }
         if (pw == 0 && lane == 0) PROBE_FLUSH(4)
     } else {
-        // =============================== CONSUMERS: the two MLPs, two tiles in flight ================================
+        // =============================== CONSUMERS: the two MLPs, activations resident in tensor memory =============
         const uint32_t ws_addr = tc::smem_u32(ws_smem), wc_addr = tc::smem_u32(wc_smem);
-        const uint32_t quarter = warp & 3u, row = quarter * 32 + lane;
-        const bool lead = warp < 4;                      // the warp of a row that handles the 16-wide output layers
-        const bool does_sh = kConsumerWarps == 4 || !lead;   // ... and the one that evaluates SH (its partner, if it has one)
+        const uint32_t quarter = warp, row = quarter * 32 + lane;
+        const uint32_t acc_all = tmem_base, opnd_all = tmem_base + kOpndCol;                 // MMA addresses (all 128 lanes)
+        const uint32_t acc = acc_all + ((quarter * 32u) << 16), opnd = opnd_all + ((quarter * 32u) << 16);   // this warp's lanes
         const uint32_t nst = ns + nc + 2;
-        uint32_t ph[kCtx] = {};
+        uint32_t ph = 0;
         PROBE_DECL
-        for (uint32_t k0 = 0;; k0 += kCtx) {
-            if (blockIdx.x + k0 * gridDim.x >= ntiles) break;
-            uint32_t b[kCtx];
-            bool has[kCtx], dead[kCtx], ok[kCtx];        // ok: this thread's row exists (ragged last tile)
-            float dx[kCtx], dy[kCtx], dz[kCtx];   // view direction of this row: its SH basis is evaluated between the two nets
-            // ---------------- take up to kCtx feature tiles and start their first layer --------------------------
-#pragma unroll
-            for (int c = 0; c < kCtx; c++) {
-                const uint32_t k = k0 + c, tile = blockIdx.x + k * gridDim.x;
-                has[c] = tile < ntiles;
-                b[c] = tile * kTileRows + row;
-                dead[c] = true; ok[c] = false; dx[c] = dy[c] = dz[c] = 0.f;
-                if (!has[c]) continue;
-                const uint32_t s = k % kStages, use = k / kStages;
-                ok[c] = b[c] < M;
-                if (ok[c] && rows) b[c] = (uint32_t)rows[b[c]];
-                dead[c] = !ok[c] || (deltas && deltas[(size_t)b[c] * 2] == 0.0f);
-                if (ok[c]) { dx[c] = dirs[(size_t)b[c] * 3]; dy[c] = dirs[(size_t)b[c] * 3 + 1]; dz[c] = dirs[(size_t)b[c] * 3 + 2]; }
-                PROBE_MARK(2)
-                // Only the issuing thread waits for the feature tile: nobody else reads it, and a consumer warp still polling
-                // full_bar[s] after the slot has been released below could see the producers complete the NEXT phase of that
-                // barrier and wait forever on a parity that has come round again.
-                if (warp == 0) { tc::mbar_wait(&full_bar[s], use & 1u); tc::tc_fence_after_sync(); }
-                PROBE_MARK(0)
+        for (uint32_t k = 0;; k++) {
+            const uint32_t tile = blockIdx.x + k * gridDim.x;
+            if (tile >= ntiles) break;
+            const uint32_t s = k % kStages, use = k / kStages;
+            uint32_t b = tile * kTileRows + row;
+            const bool ok = b < M;                        // this thread's row exists (ragged last tile)
+            if (ok && rows) b = (uint32_t)rows[b];
+            const bool dead = !ok || (deltas && deltas[(size_t)b * 2] == 0.0f);
+            float dx = 0.f, dy = 0.f, dz = 0.f;           // view direction of this row: its SH basis is evaluated between the two nets
+            if (ok) { dx = dirs[(size_t)b * 3]; dy = dirs[(size_t)b * 3 + 1]; dz = dirs[(size_t)b * 3 + 2]; }
+            PROBE_MARK(2)
+            // Only the issuing warp waits for the feature tile: nobody else reads it, and a consumer warp still polling
+            // full_bar[s] after the slot has been released below could see the producers complete the NEXT phase of that
+            // barrier and wait forever on a parity that has come round again.
+            if (warp == 0) { tc::mbar_wait(&full_bar[s], use & 1u); tc::tc_fence_after_sync(); }
+            PROBE_MARK(0)
 #ifdef NTX_DEV_PROBES
-                if (dbg & 2u) {   // producer-only timing: release the slot at once, skip both MLPs
-                    if (tid == 0) tc::mbar_arrive(&empty_bar[s]);
-                    if (ok[c]) { st_stream_f32(sigmas + b[c], 0.f); for (int q = 0; q < 3; q++) st_stream_f32(rgbs + (size_t)b[c] * 3 + q, 0.f); }
-                    has[c] = false;
-                    continue;
-                }
-#endif
-                if (warp == 0 && tc::elect_one()) {
-                    issue_layer(tc::smem_u32(a0_smem + s * plan.a0_stage), ws_addr, K0, kFW, tmem_base + c * 64u);
-                    tc::mma_commit(&mma_bar[c]);
-                    tc::mma_commit(&empty_bar[s]);   // the feature tile is free again as soon as this MMA has read it
-                }
+            if (dbg & 2u) {   // producer-only timing: release the slot at once, skip both MLPs
+                if (tid == 0) tc::mbar_arrive(&empty_bar[s]);
+                if (ok) { st_stream_f32(sigmas + b, 0.f); for (int q = 0; q < 3; q++) st_stream_f32(rgbs + (size_t)b * 3 + q, 0.f); }
+                continue;
             }
-            // ---------------- the stages, alternating between the tiles ---------------------------------------------
+#endif
+            if (warp == 0 && tc::elect_one()) {
+                issue_layer(tc::smem_u32(a0_smem + s * plan.a0_stage), ws_addr, K0, kFW, acc_all);
+                tc::mma_commit(mma_bar);
+                tc::mma_commit(&empty_bar[s]);   // the feature tile is free again as soon as this MMA has read it
+            }
             for (uint32_t st = 0; st < nst; st++) {
+                tc::mbar_wait(mma_bar, ph); ph ^= 1;
+                PROBE_MARK(1)
+                tc::tc_fence_after_sync();
+                if (st == ns) {
+                    uint32_t v[16];
+                    tc::tmem_ld_x16(acc, v);
+                    tc::tmem_wait_ld();
+                    // h = fp16(W2 . a)   (FFMLP output is fp16); sigma = trunc_exp(h[0]) = exp(float(h[0]))   (network_ff.py:88)
+                    uint32_t hb[8];
 #pragma unroll
-                for (int c = 0; c < kCtx; c++) {
-                    if (!has[c]) continue;
-                    uint8_t* h = h_smem + c * plan.h_bytes;
-                    const uint32_t acc = tmem_base + c * 64u;
-                    tc::mbar_wait(&mma_bar[c], ph[c]); ph[c] ^= 1;
-                    PROBE_MARK(1)
-                    tc::tc_fence_after_sync();
-                    if (st == ns && does_sh) {
-                        // SH of the view direction (fp32, rounded to fp16 when it enters the fp16 MLP): columns 0..15 of the colour input
-                        uint8_t* hc = h;
+                    for (int j = 0; j < 8; j++) hb[j] = float2_to_half2_bits(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                    const float h0 = __low2float(*reinterpret_cast<const __half2*>(&hb[0]));
+                    if (ok) st_stream_f32(sigmas + b, dead ? 0.0f : density_scale * expf(h0));
+                    // colour-net input [128 x 32] = SH(dir) ++ h[1..15] ++ 0   (network_ff.py:93-97) -> 16 operand columns.
+                    // SH in fp32, rounded to fp16 when it enters the fp16 MLP.
+                    uint32_t o[16];
+                    {
                         float sh[16];
-                        sh_basis<4, false>(dx[c], dy[c], dz[c], sh, nullptr, nullptr, nullptr);
-                        uint4 s0, s1;
-                        s0.x = float2_to_half2_bits(sh[0], sh[1]); s0.y = float2_to_half2_bits(sh[2], sh[3]);
-                        s0.z = float2_to_half2_bits(sh[4], sh[5]); s0.w = float2_to_half2_bits(sh[6], sh[7]);
-                        s1.x = float2_to_half2_bits(sh[8], sh[9]); s1.y = float2_to_half2_bits(sh[10], sh[11]);
-                        s1.z = float2_to_half2_bits(sh[12], sh[13]); s1.w = float2_to_half2_bits(sh[14], sh[15]);
-                        *reinterpret_cast<uint4*>(hc + kmajor_chunk_off(row, 0, kColorIn)) = s0;
-                        *reinterpret_cast<uint4*>(hc + kmajor_chunk_off(row, 1, kColorIn)) = s1;
+                        sh_basis<4, false>(dx, dy, dz, sh, nullptr, nullptr, nullptr);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) o[j] = float2_to_half2_bits(sh[2 * j], sh[2 * j + 1]);
                     }
-                    if (st == ns && lead) {
-                        uint32_t v[16];
-                        tc::tmem_ld_x16(acc + ((quarter * 32u) << 16), v);
-                        tc::tmem_wait_ld();
-                        // h = fp16(W2 . a)   (FFMLP output is fp16); sigma = trunc_exp(h[0]) = exp(float(h[0]))   (network_ff.py:88)
-                        uint32_t hb[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) hb[j] = float2_to_half2_bits(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                        const float h0 = __low2float(*reinterpret_cast<const __half2*>(&hb[0]));
-                        if (ok[c]) st_stream_f32(sigmas + b[c], dead[c] ? 0.0f : density_scale * expf(h0));
-                        // colour-net input [128 x 32] = SH(dir) ++ h[1..15] ++ 0   (network_ff.py:93-97), built at the start of this
-                        // tile's activation buffer: the hidden activations there are dead (the output-layer MMA has completed),
-                        // and the colour net's first epilogue overwrites it only after its MMA has read it.
-                        uint4 c2, c3;
-                        c2.x = __byte_perm(hb[0], hb[1], 0x5432); c2.y = __byte_perm(hb[1], hb[2], 0x5432);
-                        c2.z = __byte_perm(hb[2], hb[3], 0x5432); c2.w = __byte_perm(hb[3], hb[4], 0x5432);
-                        c3.x = __byte_perm(hb[4], hb[5], 0x5432); c3.y = __byte_perm(hb[5], hb[6], 0x5432);
-                        c3.z = __byte_perm(hb[6], hb[7], 0x5432); c3.w = __byte_perm(hb[7], 0u, 0x5432);
-                        *reinterpret_cast<uint4*>(h + kmajor_chunk_off(row, 2, kColorIn)) = c2;
-                        *reinterpret_cast<uint4*>(h + kmajor_chunk_off(row, 3, kColorIn)) = c3;
-                    } else if (st == ns) {
-                        // (partner warp of an 8-warp consumer group: SH only)
-                    } else if (st + 1 == nst) {
-                        uint32_t v[8];
-                        if (lead) { tc::tmem_ld_x8(acc + ((quarter * 32u) << 16), v); tc::tmem_wait_ld(); }
-                        if (lead && ok[c]) {
+                    for (int j = 0; j < 7; j++) o[8 + j] = __byte_perm(hb[j], hb[j + 1], 0x5432);
+                    o[15] = __byte_perm(hb[7], 0u, 0x5432);
+                    tc::tmem_st_x16(opnd, o);
+                } else if (st + 1 == nst) {
+                    uint32_t v[8];
+                    tc::tmem_ld_x8(acc, v);
+                    tc::tmem_wait_ld();
+                    if (ok) {
 #pragma unroll
-                            for (int q = 0; q < 3; q++) {
-                                // rgb = sigmoid(h) evaluated on the fp16 output in fp32 and rounded back to fp16 (torch.sigmoid on a half tensor)
-                                const float hc = __half2float(__float2half_rn(__uint_as_float(v[q])));
-                                const float sg = 1.0f / (1.0f + expf(-hc));
-                                st_stream_f32(rgbs + (size_t)b[c] * 3 + q, dead[c] ? 0.0f : __half2float(__float2half_rn(sg)));
-                            }
+                        for (int q = 0; q < 3; q++) {
+                            // rgb = sigmoid(h) evaluated on the fp16 output in fp32 and rounded back to fp16 (torch.sigmoid on a half tensor)
+                            const float hc = __half2float(__float2half_rn(__uint_as_float(v[q])));
+                            const float sg = 1.0f / (1.0f + expf(-hc));
+                            st_stream_f32(rgbs + (size_t)b * 3 + q, dead ? 0.0f : __half2float(__float2half_rn(sg)));
                         }
-                    } else {
-                        field_hidden_epilogue(acc, h, warp, lane);
                     }
-                    // epilogue done by all four warps: this tile's next layer may read the activation buffer and overwrite the
-                    // accumulator (after the last stage: the next tile in this context may)
-                    tc::fence_proxy_async_smem(); tc::tc_fence_before_sync(); consumer_sync();
-                    if (st + 1 < nst && warp == 0 && tc::elect_one()) {
-                        tc::tc_fence_after_sync();
-                        field_issue_stage(st + 1, ns, nc, K0, tc::smem_u32(h), ws_addr, wc_addr, acc);
-                        tc::mma_commit(&mma_bar[c]);
-                    }
-                    PROBE_MARK(2)
+                } else {
+                    field_hidden_epilogue(acc, opnd);
                 }
+                // epilogue done by all four warps: the next layer may read the operand columns and overwrite the accumulator
+                // (after the last stage: the next tile's first layer may)
+                tc::tmem_wait_st(); tc::tc_fence_before_sync(); consumer_sync();
+                if (st + 1 < nst && warp == 0 && tc::elect_one()) {
+                    tc::tc_fence_after_sync();
+                    field_issue_stage(st + 1, ns, nc, K0, opnd_all, ws_addr, wc_addr, acc_all);
+                    tc::mma_commit(mma_bar);
+                }
+                PROBE_MARK(2)
             }
         }
         if (tid == 0) PROBE_FLUSH(0)
