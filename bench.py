@@ -329,6 +329,13 @@ def main():
                 line["reference_cuda"] = compare_ref.main(only_frame=True)
             except Exception as e:      # never let the side measurement break the bench line
                 line["reference_cuda"] = {"unavailable": repr(e)[:200]}
+        # ---- the drop-in path: the reference's UNMODIFIED nerf/renderer.py + nerf/network_ff.py (baseline/_ref/callers) rendering the
+        #      same frame through nerf_texture_b200/compat, next to the same files on the reference's own wrappers + CUDA (oracle/_ref)
+        if world == 1:
+            line["compat"] = run_tool("run_reference_files.py", [["--backend", "ntx", "--size", str(IMG), "--time", "5"],
+                                                                 ["--backend", "ref", "--size", str(IMG), "--time", "5"]], ("ntx", "reference_cuda"), "frame_ms")
+            # ---- BASELINE config 5: training step (grid + sigma-MLP forward/backward on 2^18 samples) through the operator API
+            line["cfg5"] = run_tool("bench_cfg5.py", [["--backend", "ntx"], ["--backend", "ref"]], ("ntx", "reference_cuda"), "step_ms")
         if not args.no_cpu_baseline and world == 1:
             v, dt, ns, cores, sample = cpu_render_sample(stride=5)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "seconds": dt}
@@ -336,6 +343,23 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_tool(tool, arg_sets, names, key):
+    """run tools/<tool> once per argument set in a subprocess (the two operator stacks cannot share a process: both provide
+    `gridencoder`, `ffmlp`, ...), collect its RESULT line; speedup = reference / ntx on `key`"""
+    out = {}
+    for name, extra in zip(names, arg_sets):
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool)] + extra, capture_output=True, text=True, timeout=900)
+            res = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+            out[name] = json.loads(res[0][7:]) if res else {"unavailable": (r.stderr or r.stdout)[-300:]}
+        except Exception as e:
+            out[name] = {"unavailable": repr(e)[:200]}
+    a, b = out.get(names[0], {}), out.get(names[1], {})
+    if key in a and key in b and a[key] > 0:
+        out["speedup_vs_reference_cuda"] = b[key] / a[key]
+    return out
 
 
 def bench_cfg2(torch, L, field, device, peaks):

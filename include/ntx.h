@@ -1,7 +1,7 @@
 /* ntx.h — C ABI of libntx.so: B200 (sm_100a) kernels for NeRF-Texture's per-ray-sample hot path.
  *
  * Every entry point is `extern "C"`, takes plain device pointers + sizes + a cudaStream_t, allocates
- * nothing, never synchronises, and returns 0 on success or a negative ntx_status (no exceptions cross
+ * nothing, does not synchronise the stream (one exception: ntx_render_rays, see there) and returns 0 on success or a negative ntx_status (no exceptions cross
  * the ABI; ntx_last_error() gives the message of the calling thread's last failure).  The caller owns all
  * buffers, exactly like the reference's natives, which write into caller-allocated tensors and return void.
  * The device is the current CUDA context's.  Calls on distinct streams are thread-safe.
@@ -200,6 +200,27 @@ int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const 
                     float density_scale, float* weights_sum, float* depth, float* image, void* workspace,
                     int* host_mailbox, unsigned long long* sample_counter, uint32_t* stats_out, float* kernel_ms_out,
                     ntx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ density-grid maintenance
+ * The density-grid half of NeRFRenderer.update_extra_state (nerf/renderer.py:567-647) as one launch chain, no host round trip:
+ *   tmp_grid = -1; for every cascade: query sigma * density_scale at the grid cells (positions generated in the kernel from the
+ *   cells' Morton indices exactly as renderer.py:590-598 computes them, hash-grid gather + sigma MLP fused: the field kernel in
+ *   density mode) -> tmp_grid[cas, cell]; density_grid[valid] = max(density_grid[valid] * decay, tmp_grid[valid]);
+ *   mean_density = mean(clamp(density_grid, min=0)); packbits(density_grid, min(mean_density, density_thresh)) -> density_bitfield.
+ *   density_grid [C, H^3] f32 (in/out, Morton order per cascade), density_bitfield [C*H^3/8] u8 (out), H a power of two
+ *   cells: nullable [C, n_cells] i32 Morton indices (the partial update of renderer.py:603-625; duplicates: one of the writers wins, as
+ *     in the reference's index_put); null = every cell of every cascade (full update), n_cells ignored
+ *   noise: nullable uniform [0,1) jitter `torch.rand_like(cas_xyzs)` (renderer.py:597), [C, n, 3] f32: row = list position when
+ *     `cells` is given, else the x-major meshgrid index (x*H + y)*H + z of the cell; null = cell centres
+ *   workspace: ntx_update_density_grid_workspace_bytes(C, H) bytes, 256-byte aligned
+ *   stats_out: device [2] f32 = {mean_density, the threshold used}
+ * Field parameters as in ntx_ngp_field_forward (only the sigma net is evaluated). */
+size_t ntx_update_density_grid_workspace_bytes(uint32_t C, uint32_t H);
+int ntx_update_density_grid(float* density_grid, uint8_t* density_bitfield, uint32_t C, uint32_t H, float bound,
+                            float density_scale, float decay, float density_thresh, const void* embeddings_f16,
+                            const int* offsets, uint32_t L, float S, uint32_t base_resolution, int align_corners,
+                            const void* w_sigma_f16, const int* cells, uint32_t n_cells, const float* noise,
+                            int force_full_grid, void* workspace, float* stats_out, ntx_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -44,8 +44,10 @@ _SIGS = {
     "ntx_ngp_field_forward": [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _u32, _f32, _u32, _int, _vp, _vp, _f32, _vp, _vp, _vp],
     "ntx_render_rays": [_vp, _vp, _u32, _vp, _f32, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _u32, _f32, _u32, _int, _vp, _vp, _f32,
                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ntx_update_density_grid": [_vp, _vp, _u32, _u32, _f32, _f32, _f32, _f32, _vp, _vp, _u32, _f32, _u32, _int, _vp, _vp, _u32, _vp, _int, _vp, _vp, _vp],
 }
 _SIZE_FNS = {
+    "ntx_update_density_grid_workspace_bytes": [_u32, _u32],
     "ntx_march_rays_train_workspace_bytes": [_u32],
     "ntx_compact_rays_workspace_bytes": [_u32],
     "ntx_occupancy_mip_bytes": [_u32, _u32],
@@ -93,14 +95,20 @@ def call(name, *args):
         launches += 1
 
 
-def ptr(t):
-    """device pointer of a CUDA tensor (None -> NULL); the reference's CHECK_CUDA / CHECK_CONTIGUOUS live here"""
+def ptr(t, dtype=None):
+    """device pointer of a CUDA tensor (None -> NULL); the reference's CHECK_CUDA / CHECK_CONTIGUOUS / CHECK_IS_INT /
+    CHECK_IS_FLOATING live here: a wrong dtype or a tensor on another GPU raises instead of being reinterpreted
+    (the reference raises through data_ptr<T>() in that case)"""
     if t is None:
         return None
     if not t.is_cuda:
         raise RuntimeError("tensor must be a CUDA tensor")
     if not t.is_contiguous():
         raise RuntimeError("tensor must be a contiguous tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError("tensor must be a %s tensor (got %s)" % (str(dtype).replace("torch.", ""), str(t.dtype).replace("torch.", "")))
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError("tensor is on cuda:%d but the current device is cuda:%d" % (t.device.index, torch.cuda.current_device()))
     return t.data_ptr()
 
 

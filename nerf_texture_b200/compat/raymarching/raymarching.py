@@ -10,6 +10,8 @@ Behavioural notes (all members of the reference's own outcome set):
   * `march_rays` lets the kernel zero the unused sample slots instead of three `torch.zeros` fills per call;
   * no `torch.cuda.empty_cache()` inside `march_rays_train` (raymarching.py:226) — it only stalls the allocator.
 """
+import weakref
+
 import torch
 from torch.autograd import Function
 
@@ -18,6 +20,7 @@ from nerf_texture_b200 import _lib as L
 __all__ = ["near_far_from_aabb", "polar_from_ray", "morton3D", "morton3D_invert", "packbits", "march_rays_train",
            "march_rays_train_differentiable", "composite_rays_train", "march_rays", "composite_rays", "compact_rays"]
 
+_F32, _I32 = torch.float32, torch.int32
 _fwd32 = torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
 _bwd = torch.amp.custom_bwd(device_type="cuda")
 
@@ -89,7 +92,7 @@ def packbits(grid, thresh, bitfield=None):
     if bitfield is None:
         bitfield = _new(g, nbytes, dtype=torch.uint8)
     L.call("ntx_packbits", L.ptr(g), nbytes, float(thresh), L.ptr(bitfield), L.stream())
-    _mip_cache.pop(bitfield.data_ptr(), None)   # the bit-field changed behind torch's version counter
+    _mip_forget(bitfield)   # the bit-field changed behind torch's version counter
     return bitfield
 
 
@@ -111,7 +114,7 @@ def _march_train(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, ste
         step_counter = torch.zeros(2, dtype=torch.int32, device=o.device)
     ws = L.workspace("march_train", L.lib().ntx_march_rays_train_workspace_bytes(n), o.device)
     L.call("ntx_march_rays_train", L.ptr(o), L.ptr(d), L.ptr(bits), float(bound), float(dt_gamma), int(max_steps), n, int(C), int(H), budget, L.ptr(nears),
-           L.ptr(fars), L.ptr(xyzs), L.ptr(dirs), L.ptr(deltas), L.ptr(rays_ts), L.ptr(rays), step_counter.data_ptr(), int(bool(perturb)), L.ptr(ws), L.stream())
+           L.ptr(fars), L.ptr(xyzs), L.ptr(dirs), L.ptr(deltas), L.ptr(rays_ts), L.ptr(rays), L.ptr(step_counter, _I32), int(bool(perturb)), L.ptr(ws), L.stream())
     if force_all_rays or mean_count <= 0:
         used = step_counter[0].item()              # D2H copy, only in the first epochs (raymarching.py:219-224)
         if align > 0:
@@ -165,7 +168,7 @@ class CompositeTrainOp(Function):
         sigmas, rgbs, deltas = _f32c(sigmas), _f32c(rgbs), _f32c(deltas)
         n_samples, n_rays = sigmas.shape[0], rays.shape[0]
         weights_sum, depth, image = _new(sigmas, n_rays), _new(sigmas, n_rays), _new(sigmas, n_rays, 3)
-        L.call("ntx_composite_rays_train_forward", L.ptr(sigmas), L.ptr(rgbs), L.ptr(deltas), L.ptr(rays), n_samples, n_rays, L.ptr(weights_sum), L.ptr(depth),
+        L.call("ntx_composite_rays_train_forward", L.ptr(sigmas), L.ptr(rgbs), L.ptr(deltas), L.ptr(rays, _I32), n_samples, n_rays, L.ptr(weights_sum), L.ptr(depth),
                L.ptr(image), L.stream())
         ctx.save_for_backward(sigmas, rgbs, deltas, rays, weights_sum, image)
         return weights_sum, depth, image
@@ -185,21 +188,39 @@ composite_rays_train = CompositeTrainOp.apply
 
 
 # ---------------------------------------------------------------------------------------------------- inference
-_mip_cache = {}
+_mip_cache = {}          # id(bit-field tensor) -> (weakref to that tensor, (version, C, H), mip)
+_MIP_CACHE_MAX = 8
+
+
+def _mip_forget(bitfield):
+    _mip_cache.pop(id(bitfield), None)
 
 
 def _occupancy_mip(bitfield, C, H):
-    """conservative occupancy mip of `bitfield` (see ntx_build_occupancy_mip), cached per (storage, version): rebuilt whenever torch
-    has seen the bit-field change; our own packbits() (which writes through a raw pointer) invalidates it explicitly"""
+    """conservative occupancy mip of `bitfield` (see ntx_build_occupancy_mip).  Cached per TENSOR OBJECT (a weak reference pins the
+    identity: an entry dies with its tensor, so a new bit-field that the caching allocator places at the same address — or a
+    state_dict load into it — can never inherit another model's mip) and per version counter; our own packbits(), which writes
+    through a raw pointer, drops the entry explicitly.  Tensors without a version counter (inference mode) are not cached."""
     if H < 16 or (H & (H - 1)) != 0 or (bitfield.data_ptr() & 15) != 0:
         return None
-    key = (bitfield.data_ptr(), bitfield._version, C, H)
-    hit = _mip_cache.get(bitfield.data_ptr())
-    if hit is None or hit[0] != key:
+    try:
+        version = bitfield._version
+    except Exception:
+        version = None
+    hit = _mip_cache.get(id(bitfield)) if version is not None else None
+    if hit is not None and (hit[0]() is not bitfield or hit[1] != (version, C, H, bitfield.data_ptr())):
+        hit = None
+    if hit is None:
         mip = torch.empty(L.lib().ntx_occupancy_mip_bytes(C, H), dtype=torch.uint8, device=bitfield.device)
-        L.call("ntx_build_occupancy_mip", L.ptr(bitfield), C, H, L.ptr(mip), L.stream())
-        hit = _mip_cache[bitfield.data_ptr()] = (key, mip)
-    return hit[1].data_ptr()
+        L.call("ntx_build_occupancy_mip", L.ptr(bitfield, torch.uint8), C, H, L.ptr(mip), L.stream())
+        if version is None:
+            return mip.data_ptr(), mip
+        key = id(bitfield)
+        if len(_mip_cache) >= _MIP_CACHE_MAX:
+            for k in [k for k, v in _mip_cache.items() if v[0]() is None] or [next(iter(_mip_cache))]:
+                _mip_cache.pop(k, None)
+        hit = _mip_cache[key] = (weakref.ref(bitfield, lambda _r, key=key: _mip_cache.pop(key, None)), (version, C, H, bitfield.data_ptr()), mip)
+    return hit[2].data_ptr(), hit[2]
 
 
 @torch.no_grad()
@@ -211,17 +232,18 @@ def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, densi
     if align > 0:
         rows += align - (rows % align)
     xyzs, dirs, deltas = _new(o, rows, 3), _new(o, rows, 3), _new(o, rows, 2)     # the kernel zero-fills what it does not use
-    L.call("ntx_march_rays", int(n_alive), int(n_step), L.ptr(rays_alive), L.ptr(rays_t), L.ptr(o), L.ptr(d), float(bound), float(dt_gamma), int(max_steps),
-           int(C), int(H), L.ptr(density_bitfield), L.ptr(near), L.ptr(far), L.ptr(xyzs), L.ptr(dirs), L.ptr(deltas), int(perturb), 1, rows,
-           _occupancy_mip(density_bitfield, int(C), int(H)), L.stream())
+    mip = _occupancy_mip(density_bitfield, int(C), int(H))                          # (pointer, tensor that keeps it alive during the call)
+    L.call("ntx_march_rays", int(n_alive), int(n_step), L.ptr(rays_alive, _I32), L.ptr(rays_t, _F32), L.ptr(o), L.ptr(d), float(bound), float(dt_gamma),
+           int(max_steps), int(C), int(H), L.ptr(density_bitfield, torch.uint8), L.ptr(near, _F32), L.ptr(far, _F32), L.ptr(xyzs), L.ptr(dirs), L.ptr(deltas),
+           int(perturb), 1, rows, None if mip is None else mip[0], L.stream())
     return xyzs, dirs, deltas
 
 
 @torch.no_grad()
 def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image):
     """continues the front-to-back accumulation IN PLACE in weights_sum / depth / image; dead rays get rays_t = -1"""
-    L.call("ntx_composite_rays", int(n_alive), int(n_step), L.ptr(rays_alive), L.ptr(rays_t), L.ptr(_f32c(sigmas)), L.ptr(_f32c(rgbs)), L.ptr(_f32c(deltas)),
-           L.ptr(weights_sum), L.ptr(depth), L.ptr(image), L.stream())
+    L.call("ntx_composite_rays", int(n_alive), int(n_step), L.ptr(rays_alive, _I32), L.ptr(rays_t, _F32), L.ptr(_f32c(sigmas)), L.ptr(_f32c(rgbs)),
+           L.ptr(_f32c(deltas)), L.ptr(weights_sum, _F32), L.ptr(depth, _F32), L.ptr(image, _F32), L.stream())
     return tuple()
 
 
@@ -229,6 +251,6 @@ def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, we
 def compact_rays(n_alive, rays_alive, rays_alive_old, rays_t, rays_t_old, alive_counter):
     """survivors (rays_t_old >= 0) -> rays_alive / rays_t (ascending slot order); alive_counter += #survivors"""
     ws = L.workspace("compact", L.lib().ntx_compact_rays_workspace_bytes(int(n_alive)), rays_alive.device)
-    L.call("ntx_compact_rays", int(n_alive), L.ptr(rays_alive), L.ptr(rays_alive_old), L.ptr(rays_t), L.ptr(rays_t_old), L.ptr(alive_counter), L.ptr(ws),
-           L.stream())
+    L.call("ntx_compact_rays", int(n_alive), L.ptr(rays_alive, _I32), L.ptr(rays_alive_old, _I32), L.ptr(rays_t, _F32), L.ptr(rays_t_old, _F32),
+           L.ptr(alive_counter, _I32), L.ptr(ws), L.stream())
     return tuple()

@@ -77,6 +77,15 @@ int launch_ngp_field(const float* xyz, const float* dirs, const float* deltas, u
 // api.cu: TMA descriptor of a row-major fp16 matrix (driver entry point resolved at run time, no link-time libcuda dependency)
 int make_tensor_map_2d_f16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows);
 
+// field.cu: the same kernel over the device-driven frame's live list of (sample row, ray) entries
+int launch_ngp_field_rays(const int2* live, const int* n_live_dev, uint32_t M_bound, const float* ts, const float* rays_o, const float* rays_d, float bound,
+                          const void* embeddings_f16, const int* offsets, uint32_t L, float S, uint32_t H, int align_corners, const void* w_sigma_f16,
+                          const void* w_color_f16, float density_scale, float* sigmas, float* rgbs, cudaStream_t stream);
+// field.cu: the same kernel in density-grid maintenance mode (positions generated from Morton cell indices, sigma net only)
+int launch_density_query(uint32_t n_cells, const int* cells, const float* noise, uint32_t grid_size, float cascade_bound, float bound, const void* embeddings_f16,
+                         const int* offsets, uint32_t L, float S, uint32_t H, int align_corners, const void* w_sigma_f16, float density_scale,
+                         float* tmp_grid_cascade, cudaStream_t stream);
+
 // per-device caches of launch configuration (one process may drive several GPUs)
 constexpr int kMaxDevices = 64;
 inline int current_device() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < kMaxDevices) ? d : 0; }

@@ -120,11 +120,48 @@ __device__ __forceinline__ void field_issue_stage(uint32_t st, uint32_t ns, uint
     }
 }
 
+// What a row is: MODE_ROWS  = a row of xyz/dirs (the ntx_ngp_field_forward contract, optionally through a row list);
+//                 MODE_DENSITY = a cell of the occupancy grid (density-grid maintenance, see DensityArgs);
+//                 MODE_RAYS  = an entry (sample row, ray) of the device-driven frame's live list: the marcher stores only the
+//                              sample's ray parameter t and the field kernel rebuilds xyz = clamp(o + t d) with the marcher's own
+//                              expression (raymarching.cu:362-364) and takes the view direction from the ray — 12 instead of 32
+//                              bytes per sample leave the marcher, and xyz/dirs never exist in HBM.
+constexpr int MODE_ROWS = 0, MODE_DENSITY = 1, MODE_RAYS = 2;
+struct RayArgs {
+    const int2* live;       // [n_live] (sample row, ray index)
+    const float* ts;        // [rows] ray parameter of the sample at that row
+    const float* rays_o;    // [N,3]
+    const float* rays_d;    // [N,3]
+};
+
+// Density-grid maintenance mode (NeRFRenderer.update_extra_state, renderer.py:567-635): the samples are the cells of one cascade of
+// the occupancy grid — positions are generated in the kernel from the cell's Morton index exactly as the reference's torch code
+// computes them — only the sigma net runs, and sigma * density_scale lands in tmp_grid[cell].
+struct DensityArgs {
+    const int* cells;     // nullable: Morton index of slot i (partial update, renderer.py:603-625); null: slot i is cell i (full update)
+    const float* noise;   // nullable: uniform [0,1) jitter, [.,3]; row = slot (cells given) or x-major meshgrid index of the cell (full update)
+    uint32_t H;           // grid size
+    float inv_hm1;        // fp32 1 / (H - 1)
+    float scale;          // fp32 (bound_c - half_grid_size)
+    float hgs;            // fp32 half_grid_size = bound_c / H
+    float* tmp;           // tmp_grid of this cascade [H^3]
+};
+__device__ __forceinline__ uint32_t compact_bits3(uint32_t x) {      // raymarching.cu:75-83
+    x = x & 0x49249249u;
+    x = (x | (x >> 2)) & 0xc30c30c3u;
+    x = (x | (x >> 4)) & 0x0f00f00fu;
+    x = (x | (x >> 8)) & 0xff0000ffu;
+    x = (x | (x >> 16)) & 0x0000ffffu;
+    return x;
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
     const float* __restrict__ xyz, const float* __restrict__ dirs, const float* __restrict__ deltas, const uint32_t M_arg, const int* __restrict__ M_dev,
     const int* __restrict__ rows, const float bound, const __half* __restrict__ table, const int* __restrict__ offsets, const uint32_t L, const float S, const uint32_t H, const bool align,
     const __half* __restrict__ w_sigma, const __half* __restrict__ w_color, const uint32_t ns, const uint32_t nc, const float density_scale,
-    float* __restrict__ sigmas, float* __restrict__ rgbs, const uint32_t dbg) {
+    float* __restrict__ sigmas, float* __restrict__ rgbs, const uint32_t dbg, const DensityArgs dens, const RayArgs rays) {
+    constexpr bool DENSITY = MODE == MODE_DENSITY, RAYS = MODE == MODE_RAYS;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t M = M_dev ? (uint32_t)*M_dev : M_arg;     // device-driven frames: the sample count of this launch lives on the device
     const FieldPlan plan = field_plan(L, ns, nc);
@@ -182,17 +219,45 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
             const uint32_t srow = (task % kTasksPerTile) * kTaskRows + (lane >> 1);   // row of this lane pair inside the tile
             const uint32_t bi = tile * kTileRows + srow;
             const bool valid = bi < M;
-            const uint32_t b = (valid && rows) ? (uint32_t)rows[bi] : bi;     // row list of a device-driven frame: only rows the marcher filled
+            const uint32_t b = (MODE == MODE_ROWS && valid && rows) ? (uint32_t)rows[bi] : bi;     // optional row list
             float x = 0.f, y = 0.f, z = 0.f;
             bool skip = !valid;
-            if (valid) {
+            if (DENSITY) {
+                if (valid) {
+                    // xyzs = 2 * coords.float() / (H - 1) - 1; cas_xyzs = xyzs * (bound_c - hgs) [+ (rand * 2 - 1) * hgs]   (renderer.py:590-598)
+                    // — one rounding per torch op (a division by a Python scalar is a multiplication by its fp32 reciprocal)
+                    const uint32_t cell = dens.cells ? (uint32_t)dens.cells[bi] : bi;
+                    const uint32_t c3[3] = {compact_bits3(cell), compact_bits3(cell >> 1), compact_bits3(cell >> 2)};
+                    const size_t nrow = dens.cells ? (size_t)bi : ((size_t)c3[0] * dens.H + c3[1]) * dens.H + c3[2];
+                    float v[3];
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        v[d] = __fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn(2.0f, (float)c3[d]), dens.inv_hm1), 1.0f), dens.scale);
+                        if (dens.noise) v[d] = __fadd_rn(v[d], __fmul_rn(__fsub_rn(__fmul_rn(dens.noise[nrow * 3 + d], 2.0f), 1.0f), dens.hgs));
+                    }
+                    x = __fmul_rn(__fadd_rn(v[0], bound), inv2b);
+                    y = __fmul_rn(__fadd_rn(v[1], bound), inv2b);
+                    z = __fmul_rn(__fadd_rn(v[2], bound), inv2b);
+                }
+            } else if (RAYS) {
+                if (valid) {
+                    const int2 e = rays.live[bi];
+                    const float t = rays.ts[e.x];
+                    const float* o = rays.rays_o + (size_t)e.y * 3;
+                    const float* d = rays.rays_d + (size_t)e.y * 3;
+                    // the marcher's sample position (probe()/locate() in raymarch.cu): clamp(fma(t, d, o), -bound, bound)
+                    x = __fmul_rn(__fadd_rn(fminf(bound, fmaxf(-bound, __fmaf_rn(t, d[0], o[0]))), bound), inv2b);
+                    y = __fmul_rn(__fadd_rn(fminf(bound, fmaxf(-bound, __fmaf_rn(t, d[1], o[1]))), bound), inv2b);
+                    z = __fmul_rn(__fadd_rn(fminf(bound, fmaxf(-bound, __fmaf_rn(t, d[2], o[2]))), bound), inv2b);
+                }
+            } else if (valid) {
                 x = __fmul_rn(__fadd_rn(xyz[(size_t)b * 3], bound), inv2b);
                 y = __fmul_rn(__fadd_rn(xyz[(size_t)b * 3 + 1], bound), inv2b);
                 z = __fmul_rn(__fadd_rn(xyz[(size_t)b * 3 + 2], bound), inv2b);
                 if (deltas && deltas[(size_t)b * 2] == 0.0f) skip = true;  // sentinel slot of march_rays
             }
-            const bool oob = (x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1);
-            const bool live = !skip && !oob;
+            const uint32_t cls = skip ? 0u : sample_class(x, y, z);
+            const bool live = cls == 1u;
             if (!live) { x = 0.f; y = 0.f; z = 0.f; }  // keeps the (discarded) loads of dead lanes in bounds
             PROBE_MARK(2)
             tc::mbar_wait_relaxed(&empty_bar[s], (use & 1u) ^ 1u, 256u);   // slot free? (first use of a slot passes immediately)
@@ -204,6 +269,7 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
                 if (dbg & 1u) { packed[0] = packed[1] = 0; } else
 #endif
                 pair_gather4<__half>(x, y, z, live, p, lv + l0, half_off, packed);
+                if (cls == 2u) { packed[0] = packed[1] = nan_features<uint32_t>(); }   // NaN coordinate: NaN features like the reference
                 // lane p owns levels l0+2p, l0+2p+1 -> 4 consecutive halfs (8 bytes) of the row
                 const uint32_t kcol = 2 * (l0 + 2 * p);
                 *reinterpret_cast<uint2*>(a0 + kmajor_off(srow, kcol, K0)) = make_uint2(packed[0], packed[1]);
@@ -220,7 +286,7 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
         const uint32_t quarter = warp, row = quarter * 32 + lane;
         const uint32_t acc_all = tmem_base, opnd_all = tmem_base + kOpndCol;                 // MMA addresses (all 128 lanes)
         const uint32_t acc = acc_all + ((quarter * 32u) << 16), opnd = opnd_all + ((quarter * 32u) << 16);   // this warp's lanes
-        const uint32_t nst = ns + nc + 2;
+        const uint32_t nst = DENSITY ? ns + 1 : ns + nc + 2;      // density mode: the sigma net only
         uint32_t ph = 0;
         PROBE_DECL
         for (uint32_t k = 0;; k++) {
@@ -229,10 +295,18 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
             const uint32_t s = k % kStages, use = k / kStages;
             uint32_t b = tile * kTileRows + row;
             const bool ok = b < M;                        // this thread's row exists (ragged last tile)
-            if (ok && rows) b = (uint32_t)rows[b];
-            const bool dead = !ok || (deltas && deltas[(size_t)b * 2] == 0.0f);
             float dx = 0.f, dy = 0.f, dz = 0.f;           // view direction of this row: its SH basis is evaluated between the two nets
-            if (ok) { dx = dirs[(size_t)b * 3]; dy = dirs[(size_t)b * 3 + 1]; dz = dirs[(size_t)b * 3 + 2]; }
+            if (DENSITY) { if (ok && dens.cells) b = (uint32_t)dens.cells[b]; }
+            else if (RAYS) {
+                if (ok) {
+                    const int2 e = rays.live[b];
+                    b = (uint32_t)e.x;                     // sigma / rgb go to the sample's slot row, where composite_rays looks for them
+                    const float* d = rays.rays_d + (size_t)e.y * 3;
+                    dx = d[0]; dy = d[1]; dz = d[2];
+                }
+            } else if (ok && rows) b = (uint32_t)rows[b];
+            const bool dead = MODE == MODE_ROWS && (!ok || (deltas && deltas[(size_t)b * 2] == 0.0f));
+            if (MODE == MODE_ROWS && ok) { dx = dirs[(size_t)b * 3]; dy = dirs[(size_t)b * 3 + 1]; dz = dirs[(size_t)b * 3 + 2]; }
             PROBE_MARK(2)
             // Only the issuing warp waits for the feature tile: nobody else reads it, and a consumer warp still polling
             // full_bar[s] after the slot has been released below could see the producers complete the NEXT phase of that
@@ -264,6 +338,10 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
 #pragma unroll
                     for (int j = 0; j < 8; j++) hb[j] = float2_to_half2_bits(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
                     const float h0 = __low2float(*reinterpret_cast<const __half2*>(&hb[0]));
+                    if (DENSITY) {
+                        // sigmas = trunc_exp(h[..., 0]); sigmas *= density_scale; tmp_grid[cas, indices] = sigmas   (network_ff.py:113, renderer.py:600-602)
+                        if (ok) dens.tmp[b] = __fmul_rn(expf(h0), density_scale);
+                    } else {
                     if (ok) st_stream_f32(sigmas + b, dead ? 0.0f : density_scale * expf(h0));
                     // colour-net input [128 x 32] = SH(dir) ++ h[1..15] ++ 0   (network_ff.py:93-97) -> 16 operand columns.
                     // SH in fp32, rounded to fp16 when it enters the fp16 MLP.
@@ -278,6 +356,7 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
                     for (int j = 0; j < 7; j++) o[8 + j] = __byte_perm(hb[j], hb[j + 1], 0x5432);
                     o[15] = __byte_perm(hb[7], 0u, 0x5432);
                     tc::tmem_st_x16(opnd, o);
+                    }
                 } else if (st + 1 == nst) {
                     uint32_t v[8];
                     tc::tmem_ld_x8(acc, v);
@@ -348,6 +427,38 @@ extern "C" int ntx_ngp_field_forward(const float* xyz, const float* dirs, const 
 
 // M = upper bound of the sample count (sizes the grid); M_dev (nullable, device) = the actual count, read by the kernel;
 // rows (nullable, device) = indices of the rows to evaluate (then M counts list entries)
+template <int MODE>
+static int launch_field_kernel(const float* xyz, const float* dirs, const float* deltas, uint32_t M, const int* M_dev, const int* rows, float bound,
+                               const void* embeddings_f16, const int* offsets, uint32_t L, float S, uint32_t H, int align_corners, const void* w_sigma_f16,
+                               const void* w_color_f16, float density_scale, float* sigmas, float* rgbs, const DensityArgs& dens, const RayArgs& rays, cudaStream_t stream) {
+    const uint32_t ns = 2, nc = 3;  // FFMLP(num_layers=2) and FFMLP(num_layers=3): nerf/network_ff.py:31-49
+    const FieldPlan plan = field_plan(L, ns, nc);
+    static int occ_dev[kMaxDevices] = {};
+    static uint32_t configured_dev[kMaxDevices] = {};
+    int& occ = occ_dev[current_device()];
+    uint32_t& configured = configured_dev[current_device()];
+    if (plan.total > configured) {
+        if (cudaFuncSetAttribute(ngp_field_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("ngp_field_forward: cannot reserve %u bytes of shared memory", plan.total);
+            return NTX_ERR_CUDA;
+        }
+        configured = plan.total;
+        occ = 0;
+    }
+    if (!occ) {
+        occ = resident_ctas_per_sm((const void*)ngp_field_kernel<MODE>, kFieldThreads, plan.total, kFieldTmemCols);
+        if (tunables().field_ctas > 0) occ = std::min(occ, tunables().field_ctas);
+    }
+    const int sms = device_sm_count();
+    const uint32_t ntiles = ceil_div<uint32_t>(M, kTileRows);
+    const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)(occ * sms));
+    ngp_field_kernel<MODE><<<grid, kFieldThreads, plan.total, stream>>>(
+        xyz, dirs, deltas, M, M_dev, rows, bound, static_cast<const __half*>(embeddings_f16), offsets, L, S, H, align_corners != 0,
+        static_cast<const __half*>(w_sigma_f16), static_cast<const __half*>(w_color_f16), ns, nc, density_scale, sigmas, rgbs, dev_probe_flags(), dens, rays);
+    return check_launch(MODE == MODE_DENSITY ? "density_grid_query" : "ngp_field_forward");
+}
+
 int ntx::launch_ngp_field(const float* xyz, const float* dirs, const float* deltas, uint32_t M, const int* M_dev, const int* rows, float bound,
                           const void* embeddings_f16,
                           const int* offsets, uint32_t L, float S, uint32_t H, int align_corners, const void* w_sigma_f16, const void* w_color_f16,
@@ -357,30 +468,43 @@ int ntx::launch_ngp_field(const float* xyz, const float* dirs, const float* delt
     NTX_REQUIRE(((uintptr_t)w_sigma_f16 & 15) == 0 && ((uintptr_t)w_color_f16 & 15) == 0, NTX_ERR_INVALID_ARGUMENT, "ngp_field_forward: weights must be 16-byte aligned");
     NTX_REQUIRE(bound > 0, NTX_ERR_INVALID_ARGUMENT, "ngp_field_forward: bound must be positive");
     if (M == 0) return NTX_OK;
-    const uint32_t ns = 2, nc = 3;  // FFMLP(num_layers=2) and FFMLP(num_layers=3): nerf/network_ff.py:31-49
-    const FieldPlan plan = field_plan(L, ns, nc);
-    static int occ_dev[kMaxDevices] = {};
-    static uint32_t configured_dev[kMaxDevices] = {};
-    int& occ = occ_dev[current_device()];
-    uint32_t& configured = configured_dev[current_device()];
-    if (plan.total > configured) {
-        if (cudaFuncSetAttribute(ngp_field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess) {
-            cudaGetLastError();
-            set_error("ngp_field_forward: cannot reserve %u bytes of shared memory", plan.total);
-            return NTX_ERR_CUDA;
-        }
-        configured = plan.total;
-        occ = 0;
-    }
-    if (!occ) {
-        occ = resident_ctas_per_sm((const void*)ngp_field_kernel, kFieldThreads, plan.total, kFieldTmemCols);
-        if (tunables().field_ctas > 0) occ = std::min(occ, tunables().field_ctas);
-    }
-    const int sms = device_sm_count();
-    const uint32_t ntiles = ceil_div<uint32_t>(M, kTileRows);
-    const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)(occ * sms));
-    ngp_field_kernel<<<grid, kFieldThreads, plan.total, stream>>>(
-        xyz, dirs, deltas, M, M_dev, rows, bound, static_cast<const __half*>(embeddings_f16), offsets, L, S, H, align_corners != 0,
-        static_cast<const __half*>(w_sigma_f16), static_cast<const __half*>(w_color_f16), ns, nc, density_scale, sigmas, rgbs, dev_probe_flags());
-    return check_launch("ngp_field_forward");
+    return launch_field_kernel<MODE_ROWS>(xyz, dirs, deltas, M, M_dev, rows, bound, embeddings_f16, offsets, L, S, H, align_corners, w_sigma_f16, w_color_f16,
+                                          density_scale, sigmas, rgbs, DensityArgs{}, RayArgs{}, stream);
+}
+
+// sigma * density_scale of `n_cells` occupancy-grid cells of ONE cascade -> tmp_grid_cascade[cell]  (see DensityArgs)
+int ntx::launch_density_query(uint32_t n_cells, const int* cells, const float* noise, uint32_t grid_size, float cascade_bound, float bound, const void* embeddings_f16,
+                              const int* offsets, uint32_t L, float S, uint32_t H, int align_corners, const void* w_sigma_f16, float density_scale,
+                              float* tmp_grid_cascade, cudaStream_t stream) {
+    NTX_REQUIRE(embeddings_f16 && offsets && w_sigma_f16 && tmp_grid_cascade, NTX_ERR_INVALID_ARGUMENT, "update_density_grid: null pointer");
+    NTX_REQUIRE(L >= 8 && L <= kFieldMaxLevels && L % 8 == 0, NTX_ERR_UNSUPPORTED, "update_density_grid: num_levels must be 8, 16, 24 or 32 (got %u)", L);
+    NTX_REQUIRE(((uintptr_t)w_sigma_f16 & 15) == 0, NTX_ERR_INVALID_ARGUMENT, "update_density_grid: weights must be 16-byte aligned");
+    NTX_REQUIRE(bound > 0 && cascade_bound > 0 && grid_size >= 2 && grid_size <= 1024, NTX_ERR_INVALID_ARGUMENT, "update_density_grid: bad bound / grid size");
+    if (n_cells == 0) return NTX_OK;
+    DensityArgs d;
+    d.cells = cells; d.noise = noise; d.H = grid_size;
+    d.inv_hm1 = 1.0f / (float)(grid_size - 1);
+    const double hgs = (double)cascade_bound / (double)grid_size;       // Python floats (renderer.py:592-594), rounded to fp32 when they meet the tensor
+    d.scale = (float)((double)cascade_bound - hgs);
+    d.hgs = (float)hgs;
+    d.tmp = tmp_grid_cascade;
+    // the colour net is not evaluated in this mode; its shared-memory slot is filled from the sigma weights (any valid pointer)
+    return launch_field_kernel<MODE_DENSITY>(nullptr, nullptr, nullptr, n_cells, nullptr, nullptr, bound, embeddings_f16, offsets, L, S, H, align_corners, w_sigma_f16,
+                                             w_sigma_f16, density_scale, nullptr, nullptr, d, RayArgs{}, stream);
+}
+
+// the device-driven frame: rows = the marcher's live list (sample row, ray); M_dev = its length on the device
+int ntx::launch_ngp_field_rays(const int2* live, const int* n_live_dev, uint32_t M_bound, const float* ts, const float* rays_o, const float* rays_d, float bound,
+                               const void* embeddings_f16, const int* offsets, uint32_t L, float S, uint32_t H, int align_corners, const void* w_sigma_f16,
+                               const void* w_color_f16, float density_scale, float* sigmas, float* rgbs, cudaStream_t stream) {
+    NTX_REQUIRE(live && n_live_dev && ts && rays_o && rays_d && embeddings_f16 && offsets && w_sigma_f16 && w_color_f16 && sigmas && rgbs, NTX_ERR_INVALID_ARGUMENT,
+                "render_rays(field): null pointer");
+    NTX_REQUIRE(L >= 8 && L <= kFieldMaxLevels && L % 8 == 0, NTX_ERR_UNSUPPORTED, "ngp_field_forward: num_levels must be 8, 16, 24 or 32 (got %u)", L);
+    NTX_REQUIRE(((uintptr_t)w_sigma_f16 & 15) == 0 && ((uintptr_t)w_color_f16 & 15) == 0, NTX_ERR_INVALID_ARGUMENT, "ngp_field_forward: weights must be 16-byte aligned");
+    NTX_REQUIRE(bound > 0, NTX_ERR_INVALID_ARGUMENT, "ngp_field_forward: bound must be positive");
+    if (M_bound == 0) return NTX_OK;
+    RayArgs r;
+    r.live = live; r.ts = ts; r.rays_o = rays_o; r.rays_d = rays_d;
+    return launch_field_kernel<MODE_RAYS>(nullptr, nullptr, nullptr, M_bound, n_live_dev, nullptr, bound, embeddings_f16, offsets, L, S, H, align_corners, w_sigma_f16,
+                                          w_color_f16, density_scale, sigmas, rgbs, DensityArgs{}, r, stream);
 }

@@ -16,6 +16,8 @@
 //     every corner like c10::Half, see oracle/grid_impl.inc), so fp16 results are bit-identical to the reference.
 #include "grid_common.cuh"
 
+#include <type_traits>
+
 namespace ntx {
 
 // ---------------------------------------------------------------------------------------------------- scalar traits
@@ -154,13 +156,14 @@ __global__ void __launch_bounds__(kPairThreads, 3) grid_fwd_pair_kernel(
         const bool valid = b < B;
         float x = 0.f, y = 0.f, z = 0.f;
         if (valid) { x = inputs[(size_t)b * 3]; y = inputs[(size_t)b * 3 + 1]; z = inputs[(size_t)b * 3 + 2]; }
-        const bool oob = (x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1);
-        const bool live = valid && !oob;
+        const uint32_t cls = valid ? sample_class(x, y, z) : 0u;
+        const bool live = cls == 1u;
         if (!live) { x = 0.f; y = 0.f; z = 0.f; }  // keeps the (discarded) loads of dead lanes in bounds
 
         for (uint32_t l0 = 0; l0 < L; l0 += 4) {
             raw packed[2];
             pair_gather4<scalar_t>(x, y, z, live, p, lv + l0, half_off, packed);
+            if (cls == 2u) { packed[0] = nan_features<raw>(); packed[1] = nan_features<raw>(); }
             if (valid) {
                 const uint32_t la = l0 + 2 * p;
                 if (layout == NTX_LAYOUT_BLC) {
@@ -197,17 +200,18 @@ template <typename scalar_t, uint32_t D, uint32_t C>
 __global__ void __launch_bounds__(256) grid_bwd_kernel(
     const scalar_t* __restrict__ grad, const float* __restrict__ inputs, const int* __restrict__ offsets,
     scalar_t* __restrict__ grad_grid, const uint32_t B, const uint32_t L, const float S, const uint32_t H,
-    const uint32_t gridtype, const bool align, const int layout) {
+    const uint32_t gridtype, const bool align, const int layout, const uint32_t level0) {
     constexpr uint32_t NC = C >= 2 ? 2 : 1;  // channels per thread (gridencoder.cu:378)
     constexpr uint32_t CP = C / NC;
     extern __shared__ GridLevel lvb[];
     for (uint32_t l = threadIdx.x; l < L; l += blockDim.x) lvb[l] = make_level<D>(offsets, l, S, H, gridtype, align);
     __syncthreads();
-    const uint64_t total = (uint64_t)B * L * CP;
+    const uint32_t LN = L - level0;          // levels [level0, L): the coarse ones may have been taken by grid_bwd_small_levels_kernel
+    const uint64_t total = (uint64_t)B * LN * CP;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t cp = (uint32_t)(t % CP);
-        const uint32_t level = (uint32_t)((t / CP) % L);
-        const uint32_t b = (uint32_t)(t / ((uint64_t)CP * L));
+        const uint32_t level = level0 + (uint32_t)((t / CP) % LN);
+        const uint32_t b = (uint32_t)(t / ((uint64_t)CP * LN));
         const uint32_t ch = cp * NC;
         const GridLevel g = lvb[level];
         float x[D];
@@ -240,6 +244,58 @@ __global__ void __launch_bounds__(256) grid_bwd_kernel(
             if (NC == 2) AtomicAdd2<scalar_t>::add(gg + index, Num<scalar_t>::wmul(w, gc[0]), Num<scalar_t>::wmul(w, gc[NC - 1]));
             else AtomicAdd2<scalar_t>::add1(gg + index, Num<scalar_t>::wmul(w, gc[0]));
         }
+    }
+}
+
+// Coarse levels: a level-0 table of 4 096 entries receives 8*B updates — with one global atomic per update (the reference's
+// scheme, gridencoder.cu:296-311) the L2 serialises them per address.  Levels whose whole gradient table fits in shared memory are
+// accumulated there instead, in fp32: a CTA owns one such level and a contiguous share of the batch, adds its updates with
+// shared-memory atomics and flushes the non-zero entries with ONE global atomic each at the end (fp32 sums rounded to the table
+// dtype once per CTA: strictly more accurate than a chain of fp16 atomics).  D = 3, C = 2.
+constexpr uint32_t kBwdSmallThreads = 512;
+constexpr uint32_t kBwdSmallMaxBytes = 100u * 1024u;      // fp32 accumulators: levels with hs * 8 bytes <= this are privatised
+template <typename scalar_t>
+__global__ void __launch_bounds__(kBwdSmallThreads) grid_bwd_small_levels_kernel(
+    const scalar_t* __restrict__ grad, const float* __restrict__ inputs, const int* __restrict__ offsets, scalar_t* __restrict__ grad_grid,
+    const uint32_t B, const uint32_t L, const float S, const uint32_t H, const uint32_t gridtype, const bool align, const int layout) {
+    extern __shared__ __align__(16) float2 acc[];           // [hs] (dC0, dC1)
+    __shared__ GridLevel sg;
+    const uint32_t level = blockIdx.y;
+    if (threadIdx.x == 0) sg = make_level<3>(offsets, level, S, H, gridtype, align);
+    __syncthreads();
+    const GridLevel g = sg;
+    // the launcher sizes levels from (S, H, align); the kernel trusts only the real offsets: a level that does not fit after all
+    // is accumulated with global atomics like the fine levels (same result, just slower)
+    const bool priv = (size_t)g.hs * sizeof(float2) <= kBwdSmallMaxBytes;
+    scalar_t* gg = grad_grid + (size_t)g.offset * 2;
+    if (priv) for (uint32_t e = threadIdx.x; e < g.hs; e += blockDim.x) acc[e] = make_float2(0.f, 0.f);
+    __syncthreads();
+    const uint32_t per = ceil_div<uint32_t>(B, gridDim.x), b0 = blockIdx.x * per, b1 = min(B, b0 + per);
+    // a thread owns one (sample, corner): the 8 corners of a sample sit in 8 consecutive lanes and share its loads through L1
+    for (uint32_t t = b0 * 8u + threadIdx.x; t < b1 * 8u; t += blockDim.x) {
+        const uint32_t b = t >> 3, idx = t & 7u;
+        const float x[3] = {inputs[(size_t)b * 3], inputs[(size_t)b * 3 + 1], inputs[(size_t)b * 3 + 2]};
+        if ((x[0] < 0 || x[0] > 1) || (x[1] < 0 || x[1] > 1) || (x[2] < 0 || x[2] > 1)) continue;     // gridencoder.cu:262-270
+        float w = 1; uint32_t pl[3];
+#pragma unroll
+        for (uint32_t d = 0; d < 3; d++) {
+            const float pos = __fmaf_rn(x[d], g.scale, align ? 0.0f : 0.5f);
+            const float fl = floorf(pos);
+            const float fr = pos - fl;
+            if ((idx & (1u << d)) == 0) { w *= 1 - fr; pl[d] = (uint32_t)fl; }
+            else { w *= fr; pl[d] = (uint32_t)fl + 1; }
+        }
+        const scalar_t* gp = (layout == NTX_LAYOUT_LBC) ? grad + ((size_t)level * B + b) * 2 : grad + ((size_t)b * L + level) * 2;
+        const uint32_t index = corner_index<3>(g, pl);
+        // the reference multiplies in the table dtype (w * grad rounded to scalar_t, gridencoder.cu:306); keep that rounding point
+        const float g0 = (float)Num<scalar_t>::wmul(w, gp[0]), g1 = (float)Num<scalar_t>::wmul(w, gp[1]);
+        if (priv) { atomicAdd(&acc[index].x, g0); atomicAdd(&acc[index].y, g1); }
+        else AtomicAdd2<scalar_t>::add(gg + (size_t)index * 2, (scalar_t)g0, (scalar_t)g1);
+    }
+    __syncthreads();
+    if (priv) for (uint32_t e = threadIdx.x; e < g.hs; e += blockDim.x) {
+        const float2 v = acc[e];
+        if (v.x != 0.f || v.y != 0.f) AtomicAdd2<scalar_t>::add(gg + (size_t)e * 2, (scalar_t)v.x, (scalar_t)v.y);
     }
 }
 
@@ -336,13 +392,51 @@ static int fwd_dispatch(const float* inputs, const void* emb_, const int* offset
     return launch_fwd_generic<scalar_t, 3>(inputs, emb, offsets, out, B, C, L, S, H, cgi, dy_dx, gridtype, align, layout, st);
 }
 
+// number of leading levels (all of them must qualify) whose gradient table is accumulated in shared memory
+static uint32_t count_small_levels(const int* offsets_host, uint32_t L) {
+    uint32_t n = 0;
+    while (n < L && (size_t)(offsets_host[n + 1] - offsets_host[n]) * sizeof(float2) <= kBwdSmallMaxBytes) n++;
+    return n;
+}
+
 template <typename scalar_t, uint32_t D>
 static int launch_bwd(const scalar_t* grad, const float* inputs, const int* offsets, scalar_t* gg, uint32_t B, uint32_t C, uint32_t L, float S,
                       uint32_t H, uint32_t gridtype, bool align, int layout, cudaStream_t st) {
-    const uint64_t total = (uint64_t)B * L * (C >= 2 ? C / 2 : 1);
-    const uint32_t blocks = (uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(total, 256), 148ull * 16ull);
+    uint32_t level0 = 0;
+    if constexpr (D == 3 && !std::is_same<scalar_t, double>::value) {
+        if (C == 2 && B >= 4096) {
+            // Level sizes follow from (S, H, align, log2_hashmap_size) only, but the offsets live in device memory: recompute the
+            // first levels' sizes on the host the way GridEncoder builds them (grid.py:113-124) — dense coarse levels are
+            // min(cap, R^3) rounded up to 8 with R = ceil(2^(l*S) * H - 1) + 1 (+1 without align_corners); a level is privatised only if
+            // its dense size fits, and the kernel itself uses the real offsets, so a mismatch can only cost performance.
+            int sizes[9] = {0};
+            uint32_t n = 0;
+            for (; n < 8 && n < L; n++) {
+                const float scale = exp2f(n * S) * H - 1.0f;
+                const uint64_t res = (uint64_t)ceilf(scale) + 1, R = align ? res : res + 1;
+                const uint64_t dense = ((R * R * R + 7) / 8) * 8;
+                if (dense * sizeof(float2) > kBwdSmallMaxBytes) break;
+                sizes[n + 1] = sizes[n] + (int)dense;
+            }
+            level0 = count_small_levels(sizes, n);
+            if (level0) {
+                static bool configured_dev[kMaxDevices] = {};
+                bool& configured = configured_dev[current_device()];
+                if (!configured) {
+                    cudaFuncSetAttribute(grid_bwd_small_levels_kernel<scalar_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmallMaxBytes);
+                    configured = true;
+                }
+                const uint32_t ctas = std::max<uint32_t>(1u, (uint32_t)device_sm_count() * 2u / level0);
+                const dim3 grid(std::min<uint32_t>(ctas, ceil_div<uint32_t>(B, 256)), level0);
+                grid_bwd_small_levels_kernel<scalar_t><<<grid, kBwdSmallThreads, kBwdSmallMaxBytes, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype, align, layout);
+            }
+        }
+    }
+    if (level0 >= L) return check_launch("grid_encode_backward");
+    const uint64_t total = (uint64_t)B * (L - level0) * (C >= 2 ? C / 2 : 1);
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>(ceil_div<uint64_t>(total, 256), (uint64_t)device_sm_count() * 16ull);
     const size_t smem = sizeof(GridLevel) * L;
-#define NTX_BWD(CC) grid_bwd_kernel<scalar_t, D, CC><<<blocks, 256, smem, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype, align, layout)
+#define NTX_BWD(CC) grid_bwd_kernel<scalar_t, D, CC><<<blocks, 256, smem, st>>>(grad, inputs, offsets, gg, B, L, S, H, gridtype, align, layout, level0)
     switch (C) {
         case 1: NTX_BWD(1); break;
         case 2: NTX_BWD(2); break;

@@ -121,11 +121,24 @@ template <> struct Elem2<float> {
     static __device__ __forceinline__ raw pack(const accum& r) { return (uint64_t)__float_as_uint(r.a) | ((uint64_t)__float_as_uint(r.b) << 32); }
 };
 
+// 0: out of range (features 0, gridencoder.cu:112-121), 1: live, 2: a coordinate is NaN (features NaN, loads suppressed)
+__device__ __forceinline__ uint32_t sample_class(float x, float y, float z) {
+    const bool inside = (x >= 0 && x <= 1) && (y >= 0 && y <= 1) && (z >= 0 && z <= 1);   // false for NaN
+    const bool nan = (x != x) || (y != y) || (z != z);
+    return inside ? 1u : (nan ? 2u : 0u);
+}
+template <typename raw> __device__ __forceinline__ raw nan_features();
+template <> __device__ __forceinline__ uint32_t nan_features<uint32_t>() { return 0x7fff7fffu; }                 // two fp16 NaNs
+template <> __device__ __forceinline__ uint64_t nan_features<uint64_t>() { return 0x7fc000007fc00000ull; }     // two fp32 NaNs
+
 // A lane pair (lanes 2i, 2i+1) owns one sample; lane p (= lane & 1) gathers the four corners whose x bit is p.
 // Processes the 4 consecutive levels lv[0..3]; on return lane p holds the finished features of levels 2p and 2p+1
 // (packed[0], packed[1]), accumulated over the 8 corners in exactly the reference's order and rounding.
 // Must be called by all 32 lanes of the warp (uses shuffles).  `live` = sample valid and inside [0,1]^3; coordinates of
 // non-live samples must have been forced to 0 by the caller (their loads then hit entry 0 of each level and are discarded).
+// Callers classify with sample_class(): a NaN coordinate is NOT live (its corner indices would be arbitrary 32-bit values and
+// the dense-level fast path could read outside the table) but, as in the reference — whose `x < 0 || x > 1` test lets NaN
+// through and whose weights then are NaN (gridencoder.cu:110-121) — its features come out as NaN, not as zeros.
 template <typename scalar_t>
 __device__ __forceinline__ void pair_gather4(const float x, const float y, const float z, const bool live, const uint32_t p, const PairLevel* __restrict__ lv,
                                              const float half_off,

@@ -5,11 +5,11 @@
 //  * activation gradients ("dgrad"): one persistent tcgen05 kernel walks the layers backwards per 128-row tile with the
 //    TRANSPOSED weight matrices resident in shared memory: dH = (dOut . W) * act'(fwd), all in one kernel like the forward;
 //    every layer's dH goes to backward_buffer (the reference's layout) and optionally dL/dinput comes out at the end;
-//  * weight gradients ("wgrad"): dW[out,in] = dpre^T . act_in summed over the batch — a skinny GEMM (64x64 output, K = B).
-//    One launch per layer; each CTA reduces a slab of rows in registers (fp32) and adds its partial 64x64 to an fp32 workspace
-//    with red.global.add.f32; a last kernel rounds the workspace to fp16 once (the reference accumulates in fp16 inside CUTLASS
-//    split-K and reduces across streams).  No side streams, no events.
+//  * weight gradients ("wgrad"): dW[out,in] = dpre^T . act_in summed over the batch — a skinny GEMM (64x64 output, K = B) on
+//    tcgen05 with the batch as the UMMA reduction dimension and one fp32 accumulator in tensor memory per CTA (mlp_wgrad.cuh);
+//    per-CTA partial sums are reduced in a fixed order and rounded to fp16 once.  No side streams, no events, no atomics.
 #include "mlp_tile.cuh"
+#include "mlp_wgrad.cuh"
 
 namespace ntx {
 
@@ -186,66 +186,6 @@ __global__ void __launch_bounds__(kBwdThreads) mlp_dgrad_kernel(const __half* __
     if (warp == 0) tc::tmem_dealloc<TM_COLS>(tmem_base);
 }
 
-// ---------------------------------------------------------------------------------------------------- weight gradients
-// dW[M x N] (fp32, += ) = dY[B x M]^T . X[B x N]; M, N multiples of 16, <= 256.  CTA = 256 threads computes a 64x64 block of dW
-// (blockIdx.y / blockIdx.z select the block) over a slab of rows; each thread owns a 4x4 sub-block.
-constexpr int kWgThreads = 256;
-constexpr int kWgRowsPerStage = 32;
-
-__global__ void __launch_bounds__(kWgThreads) mlp_wgrad_kernel(const __half* __restrict__ dY, const __half* __restrict__ X, float* __restrict__ dW,
-                                                               const uint32_t B, const uint32_t M, const uint32_t N, const uint32_t rows_per_cta) {
-    __shared__ __half sA[kWgRowsPerStage][64 + 8];
-    __shared__ __half sB[kWgRowsPerStage][64 + 8];
-    const uint32_t m0 = blockIdx.y * 64, n0 = blockIdx.z * 64;
-    const uint32_t mw = min(64u, M - m0), nw = min(64u, N - n0);
-    const uint32_t tm = (threadIdx.x >> 4) * 4, tn = (threadIdx.x & 15) * 4;
-    float acc[4][4] = {};
-    const uint32_t r_begin = blockIdx.x * rows_per_cta, r_end = min(B, r_begin + rows_per_cta);
-    for (uint32_t r0 = r_begin; r0 < r_end; r0 += kWgRowsPerStage) {
-        // stage 32 rows x 64 columns of both operands (8-byte loads)
-        for (uint32_t e = threadIdx.x; e < kWgRowsPerStage * 16; e += kWgThreads) {
-            const uint32_t rr = e >> 4, c4 = (e & 15) * 4;
-            const uint32_t r = r0 + rr;
-            uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u);
-            if (r < r_end) {
-                if (c4 < mw) a = *reinterpret_cast<const uint2*>(dY + (size_t)r * M + m0 + c4);
-                if (c4 < nw) b = *reinterpret_cast<const uint2*>(X + (size_t)r * N + n0 + c4);
-            }
-            *reinterpret_cast<uint2*>(&sA[rr][c4]) = a;
-            *reinterpret_cast<uint2*>(&sB[rr][c4]) = b;
-        }
-        __syncthreads();
-#pragma unroll 8
-        for (uint32_t rr = 0; rr < kWgRowsPerStage; rr++) {
-            const float2 a01 = __half22float2(*reinterpret_cast<const __half2*>(&sA[rr][tm])), a23 = __half22float2(*reinterpret_cast<const __half2*>(&sA[rr][tm + 2]));
-            const float2 b01 = __half22float2(*reinterpret_cast<const __half2*>(&sB[rr][tn])), b23 = __half22float2(*reinterpret_cast<const __half2*>(&sB[rr][tn + 2]));
-            const float a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) acc[i][j] = __fmaf_rn(a[i], b[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (tm + i < mw && tn + j < nw) atomicAdd(dW + (size_t)(m0 + tm + i) * N + n0 + tn + j, acc[i][j]);
-}
-
-__global__ void __launch_bounds__(256) round_to_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, uint32_t n) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = __float2half_rn(src[i]);
-}
-
-static void launch_wgrad(const __half* dY, const __half* X, float* dW, uint32_t B, uint32_t M, uint32_t N, cudaStream_t st) {
-    const uint32_t target_ctas = 148 * 4 / (ceil_div<uint32_t>(M, 64) * ceil_div<uint32_t>(N, 64));
-    uint32_t rows_per_cta = std::max<uint32_t>(kWgRowsPerStage, ceil_div<uint32_t>(B, std::max<uint32_t>(target_ctas, 1)));
-    rows_per_cta = ceil_div<uint32_t>(rows_per_cta, kWgRowsPerStage) * kWgRowsPerStage;
-    const dim3 grid(ceil_div<uint32_t>(B, rows_per_cta), ceil_div<uint32_t>(M, 64), ceil_div<uint32_t>(N, 64));
-    mlp_wgrad_kernel<<<grid, kWgThreads, 0, st>>>(dY, X, dW, B, M, N, rows_per_cta);
-}
-
 template <int WIDTH>
 static int launch_dgrad(const __half* grad, const __half* w, const __half* fwd, __half* bwd, __half* gi, uint32_t B, uint32_t in_dim, uint32_t num_layers,
                         uint32_t act, cudaStream_t st) {
@@ -274,7 +214,11 @@ static int launch_dgrad(const __half* grad, const __half* w, const __half* fwd, 
 using namespace ntx;
 
 extern "C" size_t ntx_ffmlp_backward_workspace_bytes(uint32_t input_dim, uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers) {
-    return sizeof(float) * (size_t)hidden_dim * (input_dim + (size_t)hidden_dim * (num_layers - 1) + output_dim);
+    // scratch of the weight-gradient kernels: kWgMaxParts partial sums of the largest [<=128 x <=256] gradient block (the layers run
+    // one after the other on the stream and reuse it)
+    (void)num_layers;
+    const size_t widest = std::min<size_t>(256, std::max<size_t>(std::max<size_t>(input_dim, hidden_dim), output_dim));
+    return sizeof(float) * (size_t)kWgMaxParts * std::min<size_t>(hidden_dim, 128) * widest;
 }
 
 extern "C" int ntx_ffmlp_backward(const void* grad_, const void* inputs_, const void* weights_, const void* forward_buffer_, uint32_t B, uint32_t input_dim,
@@ -282,7 +226,7 @@ extern "C" int ntx_ffmlp_backward(const void* grad_, const void* inputs_, const 
                                   int calc_grad_inputs, void* backward_buffer_, void* grad_inputs_, void* grad_weights_, void* workspace_, ntx_stream_t stream) {
     (void)output_activation;   // the reference ignores it in the backward as well (ffmlp.cu:781)
     NTX_REQUIRE(grad_ && inputs_ && weights_ && forward_buffer_ && backward_buffer_ && grad_weights_, NTX_ERR_INVALID_ARGUMENT, "ffmlp_backward: null pointer");
-    NTX_REQUIRE(workspace_, NTX_ERR_WORKSPACE, "ffmlp_backward: zero-filled workspace of ntx_ffmlp_backward_workspace_bytes() bytes required");
+    NTX_REQUIRE(workspace_, NTX_ERR_WORKSPACE, "ffmlp_backward: workspace of ntx_ffmlp_backward_workspace_bytes() bytes required");
     NTX_REQUIRE(!calc_grad_inputs || grad_inputs_, NTX_ERR_INVALID_ARGUMENT, "ffmlp_backward: grad_inputs required");
     NTX_REQUIRE(input_dim > 0 && input_dim % 16 == 0, NTX_ERR_INVALID_ARGUMENT, "FFMLP input_dim should be 16 * m (m > 0), but got %u", input_dim);
     NTX_REQUIRE(output_dim == 16, NTX_ERR_UNSUPPORTED, "FFMLP current only supports output dim <= 16 (padded to 16), but got %u", output_dim);
@@ -307,15 +251,25 @@ extern "C" int ntx_ffmlp_backward(const void* grad_, const void* inputs_, const 
         default: set_error("hidden_dim should in [16, 32, 64, 128, 256]"); return NTX_ERR_UNSUPPORTED;
     }
     if (rc != NTX_OK) return rc;
-    // weight gradients (layouts as ffmlp.cu:742-748).  dpre[j] = backward_buffer[n-1-j], n = num_layers
+    // weight gradients (layouts as ffmlp.cu:742-748).  dpre[j] = backward_buffer[n-1-j], n = num_layers.  One tcgen05 kernel + its
+    // reduce per [<=128 x <=256] gradient block; the scratch is reused block after block (stream order).
     const uint32_t n = num_layers, Hd = hidden_dim;
-    float* ws0 = ws;                                             // [hidden, in]
-    float* wsh = ws + (size_t)Hd * input_dim;                    // (n-1) x [hidden, hidden]
-    float* wsl = wsh + (size_t)(n - 1) * Hd * Hd;                // [16, hidden]
-    launch_wgrad(grad, fwd + (size_t)(n - 1) * B * Hd, wsl, B, 16, Hd, st);
-    for (uint32_t j = 0; j + 1 < n; j++) launch_wgrad(bwd + (size_t)(n - 2 - j) * B * Hd, fwd + (size_t)j * B * Hd, wsh + (size_t)j * Hd * Hd, B, Hd, Hd, st);
-    launch_wgrad(bwd + (size_t)(n - 1) * B * Hd, inputs, ws0, B, Hd, input_dim, st);
-    const uint32_t nparams = Hd * (input_dim + Hd * (n - 1) + 16);
-    round_to_half_kernel<<<std::min<uint32_t>(ceil_div<uint32_t>(nparams, 256), 592u), 256, 0, st>>>(ws, gw, nparams);
-    return check_launch("ffmlp_backward(wgrad)");
+    __half* gw0 = gw;                                            // [hidden, in]
+    __half* gwh = gw + (size_t)Hd * input_dim;                   // (n-1) x [hidden, hidden]
+    __half* gwl = gwh + (size_t)(n - 1) * Hd * Hd;               // [16, hidden]
+    for (uint32_t r0 = 0; r0 < Hd; r0 += 128) {
+        const uint32_t pr = std::min<uint32_t>(128u, Hd - r0);
+        // output layer: dW_last[16 x hidden] = grad^T . act[n-1], computed as (act[n-1][:, r0:r0+pr])^T . grad and stored transposed
+        if ((rc = launch_wgrad(fwd + (size_t)(n - 1) * B * Hd + r0, Hd, pr, grad, 16, 16, true, gwl + r0, Hd, ws, B, st)) != NTX_OK) return rc;
+        // hidden layers: dW_h[j][hidden x hidden] = dpre[j+1]^T . act[j]
+        for (uint32_t j = 0; j + 1 < n; j++)
+            for (uint32_t c0 = 0; c0 < Hd; c0 += 256)
+                if ((rc = launch_wgrad(bwd + (size_t)(n - 2 - j) * B * Hd + r0, Hd, pr, fwd + (size_t)j * B * Hd + c0, Hd, std::min<uint32_t>(256u, Hd - c0), false,
+                                       gwh + (size_t)j * Hd * Hd + (size_t)r0 * Hd + c0, Hd, ws, B, st)) != NTX_OK) return rc;
+        // first layer: dW_0[hidden x in] = dpre[0]^T . inputs
+        for (uint32_t c0 = 0; c0 < input_dim; c0 += 256)
+            if ((rc = launch_wgrad(bwd + (size_t)(n - 1) * B * Hd + r0, Hd, pr, inputs + c0, input_dim, std::min<uint32_t>(256u, input_dim - c0), false,
+                                   gw0 + (size_t)r0 * input_dim + c0, input_dim, ws, B, st)) != NTX_OK) return rc;
+    }
+    return NTX_OK;
 }

@@ -448,7 +448,9 @@ __global__ void __launch_bounds__(128) morton3D_invert_kernel(const int* __restr
 }
 
 // 8 densities -> 1 byte (raymarching.cu:270-291); each thread packs 32 densities (one 32-bit word) with 128-bit loads
-__global__ void __launch_bounds__(256) packbits_kernel(const float* __restrict__ grid, const uint32_t N, const float thresh, uint8_t* __restrict__ bitfield) {
+__global__ void __launch_bounds__(256) packbits_kernel(const float* __restrict__ grid, const uint32_t N, float thresh, uint8_t* __restrict__ bitfield,
+                                                       const float* __restrict__ thresh_dev) {
+    if (thresh_dev) thresh = *thresh_dev;       // threshold produced on the device by the kernel before (density-grid maintenance)
     const uint32_t words = N / 4;
     for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) {
         const uint4* src = reinterpret_cast<const uint4*>(grid + (size_t)w * 32);
@@ -465,8 +467,9 @@ __global__ void __launch_bounds__(256) packbits_kernel(const float* __restrict__
     }
     // tail bytes (N not a multiple of 4) and unaligned inputs are handled by the scalar kernel below
 }
-__global__ void __launch_bounds__(128) packbits_scalar_kernel(const float* __restrict__ grid, const uint32_t n0, const uint32_t N, const float thresh,
-                                                              uint8_t* __restrict__ bitfield) {
+__global__ void __launch_bounds__(128) packbits_scalar_kernel(const float* __restrict__ grid, const uint32_t n0, const uint32_t N, float thresh,
+                                                              uint8_t* __restrict__ bitfield, const float* __restrict__ thresh_dev) {
+    if (thresh_dev) thresh = *thresh_dev;
     const uint32_t n = n0 + threadIdx.x + blockIdx.x * blockDim.x;
     if (n >= N) return;
     uint8_t bits = 0;
@@ -1002,14 +1005,83 @@ extern "C" int ntx_morton3D_invert(const int* indices, uint32_t N, int* coords, 
     return check_launch("morton3D_invert");
 }
 
+static int launch_packbits(const float* grid, uint32_t N, float density_thresh, const float* thresh_dev, uint8_t* bitfield, cudaStream_t st) {
+    const bool aligned = ((reinterpret_cast<uintptr_t>(grid) & 15) == 0) && ((reinterpret_cast<uintptr_t>(bitfield) & 3) == 0);
+    const uint32_t vec_bytes = aligned ? (N / 4) * 4 : 0;
+    if (vec_bytes) packbits_kernel<<<min(ceil_div<uint32_t>(vec_bytes / 4, 256), (uint32_t)device_sm_count() * 8u), 256, 0, st>>>(grid, vec_bytes, density_thresh, bitfield, thresh_dev);
+    if (vec_bytes < N) packbits_scalar_kernel<<<ceil_div<uint32_t>(N - vec_bytes, 128), 128, 0, st>>>(grid, vec_bytes, N, density_thresh, bitfield, thresh_dev);
+    return check_launch("packbits");
+}
+
 extern "C" int ntx_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, ntx_stream_t stream) {
     NTX_REQUIRE(grid && bitfield, NTX_ERR_INVALID_ARGUMENT, "packbits: null pointer");
     if (N == 0) return NTX_OK;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(grid) & 15) == 0) && ((reinterpret_cast<uintptr_t>(bitfield) & 3) == 0);
-    const uint32_t vec_bytes = aligned ? (N / 4) * 4 : 0;
-    if (vec_bytes) packbits_kernel<<<min(ceil_div<uint32_t>(vec_bytes / 4, 256), 148u * 8u), 256, 0, ST(stream)>>>(grid, vec_bytes, density_thresh, bitfield);
-    if (vec_bytes < N) packbits_scalar_kernel<<<ceil_div<uint32_t>(N - vec_bytes, 128), 128, 0, ST(stream)>>>(grid, vec_bytes, N, density_thresh, bitfield);
-    return check_launch("packbits");
+    return launch_packbits(grid, N, density_thresh, nullptr, bitfield, ST(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------- density-grid maintenance
+// NeRFRenderer.update_extra_state (nerf/renderer.py:567-660) as one launch chain on the stream, no host round trip:
+//   tmp = -1  ->  per cascade: fused field kernel in density mode (positions from Morton cell indices, hash-grid gather + sigma MLP,
+//   sigma * density_scale -> tmp[cell])  ->  EMA-max into density_grid + sum of clamp(grid, 0)  ->  threshold = min(mean, density_thresh)
+//   ->  packbits with that device-side threshold.
+namespace ntx {
+__global__ void __launch_bounds__(256) fill_f32_kernel(float* __restrict__ p, const uint32_t n, const float v) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
+}
+// density_grid[valid] = max(density_grid[valid] * decay, tmp[valid]), valid = (density_grid >= 0) & (tmp >= 0)  (renderer.py:637-641);
+// stats[0] += sum(clamp(density_grid, min=0)) in double
+__global__ void __launch_bounds__(256) density_ema_kernel(float* __restrict__ grid, const float* __restrict__ tmp, const uint32_t n, const float decay,
+                                                          const bool force_full_grid, double* __restrict__ stats) {
+    __shared__ double s_sum[8];
+    double local = 0.0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float g = grid[i];
+        const float t = tmp[i];
+        if (force_full_grid || (g >= 0 && t >= 0)) { g = fmaxf(__fmul_rn(g, decay), t); grid[i] = g; }
+        local += (double)fmaxf(g, 0.0f);
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += s_sum[w];
+        atomicAdd(stats, t);
+    }
+}
+// stats_out = {mean_density, threshold = min(mean_density, density_thresh)}   (renderer.py:642-647)
+__global__ void density_finalize_kernel(const double* __restrict__ stats, const uint32_t n, const float density_thresh, float* __restrict__ out2) {
+    const float mean = (float)(stats[0] / (double)n);
+    out2[0] = mean;
+    out2[1] = fminf(mean, density_thresh);
+}
+}  // namespace ntx
+
+extern "C" size_t ntx_update_density_grid_workspace_bytes(uint32_t C, uint32_t H) { return sizeof(float) * (size_t)C * H * H * H + 256; }
+
+extern "C" int ntx_update_density_grid(float* density_grid, uint8_t* density_bitfield, uint32_t C, uint32_t H, float bound, float density_scale, float decay,
+                                       float density_thresh, const void* embeddings_f16, const int* offsets, uint32_t L, float S, uint32_t base_resolution,
+                                       int align_corners, const void* w_sigma_f16, const int* cells, uint32_t n_cells, const float* noise, int force_full_grid,
+                                       void* workspace, float* stats_out, ntx_stream_t stream) {
+    NTX_REQUIRE(density_grid && density_bitfield && workspace && stats_out, NTX_ERR_INVALID_ARGUMENT, "update_density_grid: null pointer");
+    NTX_REQUIRE(C >= 1 && C <= 16 && H >= 2 && H <= 1024 && (H & (H - 1)) == 0, NTX_ERR_INVALID_ARGUMENT, "update_density_grid: C in [1,16], H a power of two <= 1024");
+    NTX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, NTX_ERR_INVALID_ARGUMENT, "update_density_grid: workspace must be 256-byte aligned");
+    cudaStream_t st = ST(stream);
+    const uint32_t H3 = H * H * H, total = C * H3;
+    double* stats = static_cast<double*>(workspace);                       // [1] sum of clamp(grid, 0)
+    float* tmp = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
+    cudaMemsetAsync(stats, 0, sizeof(double), st);
+    fill_f32_kernel<<<min(ceil_div<uint32_t>(total, 256), (uint32_t)device_sm_count() * 8u), 256, 0, st>>>(tmp, total, -1.0f);   // tmp_grid = -ones_like (renderer.py:575)
+    const uint32_t per = cells ? n_cells : H3;
+    for (uint32_t cas = 0; cas < C; cas++) {
+        const float cb = fminf((float)(1u << cas), bound);                // bound = min(2 ** cas, self.bound)   (renderer.py:592)
+        const int rc = launch_density_query(per, cells ? cells + (size_t)cas * n_cells : nullptr, noise ? noise + (size_t)cas * per * 3 : nullptr, H, cb, bound,
+                                            embeddings_f16, offsets, L, S, base_resolution, align_corners, w_sigma_f16, density_scale, tmp + (size_t)cas * H3, st);
+        if (rc != NTX_OK) return rc;
+    }
+    density_ema_kernel<<<min(ceil_div<uint32_t>(total, 256), (uint32_t)device_sm_count() * 8u), 256, 0, st>>>(density_grid, tmp, total, decay, force_full_grid != 0, stats);
+    density_finalize_kernel<<<1, 1, 0, st>>>(stats, total, density_thresh, stats_out);
+    return launch_packbits(density_grid, total / 8, 0.0f, stats_out + 1, density_bitfield, st);
 }
 
 static size_t scan_ws_bytes(uint32_t nblocks) { return sizeof(uint32_t) * 2 + sizeof(unsigned long long) * (size_t)(nblocks ? nblocks : 1); }

@@ -42,6 +42,26 @@ _GridGeom = namedtuple("_GridGeom", "B D C L S H gridtype align want_dx")
 GRIDTYPE_ID = {"hash": 0, "tiled": 1}          # gridencoder/grid.py:14-17
 
 
+def _half_table(embeddings):
+    """fp16 copy of the table, kept on the tensor object and re-made only when torch has seen the table change (version counter) or
+    move (data pointer).  The reference casts all 12.2 M entries on EVERY call under autocast (gridencoder/grid.py:38-39) — 43 times
+    per rendered frame; an optimizer step bumps the version, so training still casts once per step, exactly when it has to."""
+    if embeddings.dtype == _HALF:
+        return embeddings
+    try:
+        key = (embeddings._version, embeddings.data_ptr(), tuple(embeddings.shape))
+    except Exception:                       # inference-mode tensors have no version counter: no caching
+        return embeddings.to(_HALF)
+    hit = getattr(embeddings, "_ntx_half_table", None)
+    if hit is None or hit[0] != key:
+        hit = (key, embeddings.detach().to(_HALF))
+        try:
+            embeddings._ntx_half_table = hit
+        except Exception:
+            pass
+    return hit[1]
+
+
 class HashGridOp(Function):
     """grid_encode (gridencoder/grid.py:19-87): x in [0,1]^D, table [n_entries, C], offsets [L+1] -> features [B, L*C]"""
 
@@ -50,7 +70,7 @@ class HashGridOp(Function):
     def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False, gridtype=0, align_corners=False):
         x = _dense(inputs, _F32)
         # under autocast the table (not the coordinates) goes to half, and only for even C (gridencoder/grid.py:36-39)
-        table = embeddings.to(_HALF) if (torch.is_autocast_enabled() and embeddings.shape[1] % 2 == 0) else embeddings
+        table = _half_table(embeddings) if (torch.is_autocast_enabled() and embeddings.shape[1] % 2 == 0) else embeddings
         table = table.contiguous()
         g = _GridGeom(x.shape[0], x.shape[1], table.shape[1], offsets.shape[0] - 1, float(np.log2(per_level_scale)), int(base_resolution),
                       int(gridtype), int(align_corners), bool(calc_grad_inputs))
@@ -162,7 +182,7 @@ class FusedMLPOp(Function):
         d_w = torch.zeros_like(w)
         d_x = torch.zeros_like(x) if g.want_dx else torch.zeros(1, device=dy.device, dtype=dy.dtype)
         d_hidden = _scratch(dy, g.depth, g.B, g.width)
-        ws = torch.zeros(L.lib().ntx_ffmlp_backward_workspace_bytes(g.n_in, g.n_out, g.width, g.depth), dtype=torch.uint8, device=dy.device)
+        ws = torch.empty(L.lib().ntx_ffmlp_backward_workspace_bytes(g.n_in, g.n_out, g.width, g.depth), dtype=torch.uint8, device=dy.device)
         L.call("ntx_ffmlp_backward", L.ptr(dy), L.ptr(x), L.ptr(w), L.ptr(hidden), g.B, g.n_in, g.n_out, g.width, g.depth, g.act, g.out_act, int(g.want_dx),
                L.ptr(d_hidden), L.ptr(d_x), L.ptr(d_w), L.ptr(ws), L.stream())
         return (d_x if g.want_dx else None), d_w, None, None, None, None, None, None, None, None

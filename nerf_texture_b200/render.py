@@ -105,7 +105,11 @@ def _frame_buffers(dev, N, max_steps, budget, mailbox_len):
         mailbox = torch.zeros(mailbox_len, dtype=torch.int32).pin_memory()
         counter = torch.zeros(1, dtype=torch.int64, device=dev)
         buf = (ws, ws.data_ptr() + off, mailbox, counter)
-        _frame_cache.clear()          # one frame size at a time is the normal case; do not hoard workspaces
+        # One frame size at a time is the normal case: do not hoard workspaces.  A workspace being evicted may still be in use by a
+        # frame queued on ITS stream (the key holds the stream): wait for that device's work before the allocator may recycle it.
+        if _frame_cache:
+            torch.cuda.synchronize(dev)
+            _frame_cache.clear()
         _frame_cache[key] = buf
     return buf
 

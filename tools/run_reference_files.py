@@ -101,8 +101,9 @@ def import_reference_network(backend):
     import torch  # noqa: F401  (must be loaded before the extensions)
     warnings.filterwarnings("ignore", category=FutureWarning)     # torch.cuda.amp.custom_fwd deprecation in the reference's files
     sys.meta_path.insert(0, _StubFinder())
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)                                   # nerf_texture_b200.scene (test scene) — NOT the compat packages
     if backend == "ntx":
-        sys.path.insert(0, ROOT)
         import nerf_texture_b200
         nerf_texture_b200.install()                                # compat/ first on sys.path: gridencoder, ffmlp, ... resolve to libntx
     else:
