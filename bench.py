@@ -214,9 +214,13 @@ def main():
     else:
         my_o, my_d = rays_o, rays_d
 
+    n_max = render._shard_plan(N, world, 1024, device)[1] if world > 1 else None
+
     def step_device():
-        out = render.render_rays(field, my_o, my_d, bits, 1, 128)     # this rank's (resident) shard of the frame
-        return render.gather_frame(out, N) if world > 1 else out      # + the tile all-gather (config 4)
+        # this rank's (resident) shard of the frame, rendered straight into its planar send block, + the tile all-gather and the
+        # assembly kernel (config 4); one GPU: the frame
+        out = render.render_rays(field, my_o, my_d, bits, 1, 128, block_rows=n_max)
+        return render.gather_frame(out, N) if world > 1 else out
 
     def barrier():
         if world > 1:
@@ -266,7 +270,7 @@ def main():
 
     def step_e2e():
         d_o.copy_(h_o, non_blocking=True); d_d.copy_(h_d, non_blocking=True)
-        out = render.render_rays(field, d_o, d_d, bits, 1, 128)       # each rank uploads and renders its own shard
+        out = render.render_rays(field, d_o, d_d, bits, 1, 128, block_rows=n_max)       # each rank uploads and renders its own shard
         if world > 1:
             out = render.gather_frame(out, N)
         if rank == 0:
@@ -283,11 +287,29 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": "render_1024x1024_network_ff_random_weights (BASELINE config 3%s)" % ("; rays sharded in interleaved 1024-ray tiles + one NCCL all_gather, config 4" if world > 1 else ""),
                    "field": "hashgrid L=16 T=2^19 F=2 fp16 -> FFMLP(32,16,64,2) -> SH4 -> FFMLP(32,3,64,3)", "rays": N, "samples_per_frame": samples_per_frame,
-                   "loop_iterations": iterations, "sample_schedule": "n_step = clamp(8N // n_alive, 1, 64), walk budget %d (same image as the reference's clamp(N // n_alive, 1, 8): 43 iterations)" % render.WALK_BUDGET,
+                   "loop_iterations": iterations, "sample_schedule": "n_step = clamp(8N // n_alive, 1, 64) rounded to 4, walk budget %d, rays that cannot reach an occupied cell dropped before the first march (same image as the reference's clamp(N // n_alive, 1, 8): 43 iterations)" % render.WALK_BUDGET,
                    "max_steps": 1024, "dt_gamma": 0, "occupancy": "ball r=0.5, H=128, 1 cascade",
                    "l2": "flushed between timed steps (256 MiB memset)", "parallelism": "ray-sharded x%d" % world},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
+
+    # ---- where a rank's time goes at this N (SCALE runs): march / field kernel sums of one frame (CUDA events inside
+    #      ntx_render_rays), the rank's whole shard, and the all-gather + assembly — every rank reports, rank 0 prints
+    if world > 1:
+        flush.zero_()
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        o = render.render_rays(field, my_o, my_d, bits, 1, 128, time_kernels=True, block_rows=n_max)
+        ev[1].record()
+        render.gather_frame(o, N)
+        ev[2].record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([o["march_ms"], o["field_ms"], ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), float(o["iterations"])], dtype=torch.float32, device=device)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        line["per_rank_ms"] = [{"rank": r, "march_ms": round(float(v[0]), 3), "field_ms": round(float(v[1]), 3), "shard_ms": round(float(v[2]), 3),
+                                "gather_ms": round(float(v[3]), 3), "iterations": int(v[4])} for r, v in enumerate(allr)]
 
     if rank == 0 and not args.no_extras:
         peaks, peak_src = measured_peaks()

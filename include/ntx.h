@@ -201,6 +201,13 @@ int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const 
                     int* host_mailbox, unsigned long long* sample_counter, uint32_t* stats_out, float* kernel_ms_out,
                     ntx_stream_t stream);
 
+/* Epilogue of a ray-sharded frame (BASELINE config 4): rank r rendered the interleaved tiles k = r, r + world, ... (tile rays each)
+ * into a planar block [weights_sum (n_max) | depth (n_max) | rgb (3 n_max)] f32; `gathered` = the world blocks after ONE all-gather.
+ * Puts every ray back at its image position and adds the background term image + (1 - weights_sum) * bg (renderer.py:485).
+ * world = 1: the single-GPU epilogue. */
+int ntx_unshard_frame(const float* gathered, uint32_t world, uint32_t n_max, uint32_t tile, uint32_t N, float bg,
+                      float* image, float* depth, float* weights_sum, ntx_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------ density-grid maintenance
  * The density-grid half of NeRFRenderer.update_extra_state (nerf/renderer.py:567-647) as one launch chain, no host round trip:
  *   tmp_grid = -1; for every cascade: query sigma * density_scale at the grid cells (positions generated in the kernel from the

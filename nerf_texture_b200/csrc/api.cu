@@ -18,7 +18,6 @@ const Tunables& tunables() {
         const char* e;
         v.field_ctas = (e = getenv("NTX_FIELD_CTAS")) ? atoi(e) : 0;
         v.pair_ctas = (e = getenv("NTX_PAIR_CTAS")) ? atoi(e) : 0;
-        v.mlp_impl = (e = getenv("NTX_MLP_IMPL")) ? atoi(e) : 0;
         return v;
     }();
     return t;

@@ -26,7 +26,6 @@ void set_error(const char* fmt, ...);
 struct Tunables {
     int field_ctas;          // NTX_FIELD_CTAS: resident CTAs per SM of the fused field kernel (0 = as many as fit)
     int pair_ctas;           // NTX_PAIR_CTAS: same for the stand-alone pair gather kernel
-    int mlp_impl;            // NTX_MLP_IMPL: 0 = pipelined kernel (TMA ring, activations in tensor memory), 1 = round-1 kernel (A/B measurements)
 };
 const Tunables& tunables();
 

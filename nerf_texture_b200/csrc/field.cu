@@ -245,10 +245,14 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
                     const float t = rays.ts[e.x];
                     const float* o = rays.rays_o + (size_t)e.y * 3;
                     const float* d = rays.rays_d + (size_t)e.y * 3;
-                    // the marcher's sample position (probe()/locate() in raymarch.cu): clamp(fma(t, d, o), -bound, bound)
-                    x = __fmul_rn(__fadd_rn(fminf(bound, fmaxf(-bound, __fmaf_rn(t, d[0], o[0]))), bound), inv2b);
-                    y = __fmul_rn(__fadd_rn(fminf(bound, fmaxf(-bound, __fmaf_rn(t, d[1], o[1]))), bound), inv2b);
-                    z = __fmul_rn(__fadd_rn(fminf(bound, fmaxf(-bound, __fmaf_rn(t, d[2], o[2]))), bound), inv2b);
+                    // the marcher's sample position, written exactly like probe()/locate() in raymarch.cu (and raymarching.cu:362-364)
+                    // so that the compiler contracts it the same way: clamp(o + t * d, -bound, bound)
+                    const float sx = fminf(bound, fmaxf(-bound, o[0] + t * d[0]));
+                    const float sy = fminf(bound, fmaxf(-bound, o[1] + t * d[1]));
+                    const float sz = fminf(bound, fmaxf(-bound, o[2] + t * d[2]));
+                    x = __fmul_rn(__fadd_rn(sx, bound), inv2b);
+                    y = __fmul_rn(__fadd_rn(sy, bound), inv2b);
+                    z = __fmul_rn(__fadd_rn(sz, bound), inv2b);
                 }
             } else if (valid) {
                 x = __fmul_rn(__fadd_rn(xyz[(size_t)b * 3], bound), inv2b);

@@ -2,159 +2,16 @@
 // Replaces ffmlp/src/ffmlp.cu: kernel_mlp_fused (:332, wmma m16n16k16 with fp16 accumulators, weights re-read from
 // L2 by each of 8192 CTAs) and kernel_mlp_fused_backward (:411) + the CUTLASS split-K weight-gradient GEMMs (:804-875).
 //
-// Forward / inference: persistent CTAs, all weight matrices resident in shared memory for the CTA's lifetime, one
-// 128-row tile at a time through  UMMA(M=128,N=hidden,K=16) -> TMEM -> ReLU/fp16 epilogue -> smem -> next UMMA.
-// Accumulation is fp32 (TMEM); activations are rounded to fp16 once per layer, as in the reference.
+// Forward / inference: persistent CTAs, all weight matrices resident in shared memory for the CTA's lifetime; input tiles arrive
+// through a TMA ring, hidden activations stay in tensor memory between the layers (tcgen05.mma with the A operand in TMEM), two
+// 128-row tiles in flight per CTA, everything synchronised with mbarriers (see mlp_pipe_kernel).  Accumulation is fp32 (TMEM);
+// activations are rounded to fp16 once per layer, as in the reference.
 #include "mlp_tile.cuh"
 
 namespace ntx {
 
-constexpr int kMlpThreads = 256;
-
-struct MlpSmemPlan {
-    uint32_t w_bytes, a0_off, h_off, misc_off, total;
-};
-__host__ __device__ inline MlpSmemPlan mlp_smem_plan(uint32_t in_dim, uint32_t hidden, uint32_t num_layers) {
-    MlpSmemPlan p;
-    p.w_bytes = 2u * (hidden * in_dim + (num_layers - 1) * hidden * hidden + 16u * hidden);
-    p.a0_off = (p.w_bytes + 127u) & ~127u;
-    p.h_off = p.a0_off + kTileRows * in_dim * 2u;
-    p.misc_off = p.h_off + kTileRows * hidden * 2u;
-    p.total = p.misc_off + 64u;
-    return p;
-}
-
-// epilogue of a hidden layer: TMEM [128 x WIDTH] fp32 -> activation -> fp16 -> smem A tile (+ optional global copy)
-template <int WIDTH>
-__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_base, uint8_t* h_smem, uint32_t act, __half* __restrict__ gdst /* row-major [*,WIDTH] of this tile or null */,
-                                                uint32_t rows_valid) {
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t q = warp & 3, half_sel = warp >> 2;
-    const uint32_t row = q * 32 + lane;
-    constexpr int CPT = WIDTH / 2;                 // columns per thread
-    constexpr int CH = CPT < 32 ? CPT : 32;        // columns per TMEM load
-#pragma unroll
-    for (int c0 = 0; c0 < CPT; c0 += CH) {
-        const uint32_t col = half_sel * CPT + c0;
-        uint32_t v[CH];
-        const uint32_t taddr = tmem_base + ((q * 32u) << 16) + col;
-        if (CH == 32) tc::tmem_ld_x32(taddr, v);
-        else if (CH == 16) tc::tmem_ld_x16(taddr, v);
-        else tc::tmem_ld_x8(taddr, v);
-        tc::tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < CH; j += 8) {
-            uint4 o;
-            o.x = act_pack2(act, v[j + 0], v[j + 1]);
-            o.y = act_pack2(act, v[j + 2], v[j + 3]);
-            o.z = act_pack2(act, v[j + 4], v[j + 5]);
-            o.w = act_pack2(act, v[j + 6], v[j + 7]);
-            *reinterpret_cast<uint4*>(h_smem + kmajor_chunk_off(row, (col + j) >> 3, WIDTH)) = o;
-            if (gdst && row < rows_valid) st_stream_u4(gdst + (size_t)row * WIDTH + col + j, o);
-        }
-    }
-}
-
-template <int WIDTH, bool TRAIN>
-__global__ void __launch_bounds__(kMlpThreads) mlp_fused_kernel(const __half* __restrict__ inputs, const __half* __restrict__ weights,
-                                                                __half* __restrict__ outputs, __half* __restrict__ fwd_buf, const uint32_t B,
-                                                                const uint32_t in_dim, const uint32_t num_layers, const uint32_t act,
-                                                                const uint32_t out_act) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const MlpSmemPlan plan = mlp_smem_plan(in_dim, WIDTH, num_layers);
-    uint8_t* w_smem = smem;
-    uint8_t* a0_smem = smem + plan.a0_off;
-    uint8_t* h_smem = smem + plan.h_off;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + plan.misc_off);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + plan.misc_off + 16);
-    constexpr uint32_t TM_COLS = WIDTH < 32 ? 32 : WIDTH;
-
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t n_hidden = num_layers - 1;  // hidden x hidden matmuls (ffmlp.cu:574)
-
-    // ---- one-time setup: barrier, TMEM, weights -> smem (core-matrix layout) ------------------------------------
-    if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_mbar_init(); }
-    if (warp == 0) tc::tmem_alloc<TM_COLS>(tmem_slot);
-    {
-        const __half* w = weights;
-        uint8_t* dst = w_smem;
-        load_matrix_kmajor(dst, w, WIDTH, in_dim, tid, kMlpThreads);
-        w += (size_t)WIDTH * in_dim; dst += (size_t)WIDTH * in_dim * 2;
-        for (uint32_t k = 0; k < n_hidden; k++) {
-            load_matrix_kmajor(dst, w, WIDTH, WIDTH, tid, kMlpThreads);
-            w += (size_t)WIDTH * WIDTH; dst += (size_t)WIDTH * WIDTH * 2;
-        }
-        load_matrix_kmajor(dst, w, 16, WIDTH, tid, kMlpThreads);
-    }
-    tc::fence_proxy_async_smem();
-    tc::tc_fence_before_sync();
-    __syncthreads();
-    tc::tc_fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t w_addr = tc::smem_u32(w_smem), a0_addr = tc::smem_u32(a0_smem), h_addr = tc::smem_u32(h_smem);
-    const uint32_t w_hidden_addr = w_addr + WIDTH * in_dim * 2u;
-    const uint32_t w_last_addr = w_hidden_addr + n_hidden * WIDTH * WIDTH * 2u;
-    uint32_t phase = 0;
-
-    const uint32_t ntiles = ceil_div<uint32_t>(B, kTileRows);
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const size_t row0 = (size_t)tile * kTileRows;
-        const uint32_t rows_valid = (uint32_t)min((size_t)kTileRows, (size_t)B - row0);
-        load_rows_kmajor_stream(a0_smem, inputs + row0 * in_dim, kTileRows, rows_valid, in_dim, tid, kMlpThreads);
-        tc::fence_proxy_async_smem();
-        __syncthreads();
-
-        // first layer: [128 x in_dim] . W0^T
-        if (warp == 0 && tc::elect_one()) { tc::tc_fence_after_sync(); issue_layer(a0_addr, w_addr, in_dim, WIDTH, tmem_base); tc::mma_commit(bar); }
-        tc::mbar_wait(bar, phase); phase ^= 1;
-        tc::tc_fence_after_sync();
-        hidden_epilogue<WIDTH>(tmem_base, h_smem, act, TRAIN ? fwd_buf + ((size_t)0 * B + row0) * WIDTH : nullptr, rows_valid);
-        tc::fence_proxy_async_smem();
-        tc::tc_fence_before_sync();
-        __syncthreads();
-
-        // hidden layers, in place: the MMA that read h_smem has completed before the epilogue overwrites it
-        for (uint32_t k = 0; k < n_hidden; k++) {
-            if (warp == 0 && tc::elect_one()) { tc::tc_fence_after_sync(); issue_layer(h_addr, w_hidden_addr + k * WIDTH * WIDTH * 2u, WIDTH, WIDTH, tmem_base); tc::mma_commit(bar); }
-            tc::mbar_wait(bar, phase); phase ^= 1;
-            tc::tc_fence_after_sync();
-            hidden_epilogue<WIDTH>(tmem_base, h_smem, act, TRAIN ? fwd_buf + ((size_t)(k + 1) * B + row0) * WIDTH : nullptr, rows_valid);
-            tc::fence_proxy_async_smem();
-            tc::tc_fence_before_sync();
-            __syncthreads();
-        }
-
-        // output layer: N = 16 (ffmlp.py:118 pads output_dim to 16)
-        if (warp == 0 && tc::elect_one()) { tc::tc_fence_after_sync(); issue_layer(h_addr, w_last_addr, WIDTH, 16, tmem_base); tc::mma_commit(bar); }
-        tc::mbar_wait(bar, phase); phase ^= 1;
-        tc::tc_fence_after_sync();
-        if (warp < 4) {
-            uint32_t v[16];
-            tc::tmem_ld_x16(tmem_base + ((warp * 32u) << 16), v);
-            tc::tmem_wait_ld();
-            uint4 o0, o1;
-            o0.x = act_pack2(out_act, v[0], v[1]);   o0.y = act_pack2(out_act, v[2], v[3]);
-            o0.z = act_pack2(out_act, v[4], v[5]);   o0.w = act_pack2(out_act, v[6], v[7]);
-            o1.x = act_pack2(out_act, v[8], v[9]);   o1.y = act_pack2(out_act, v[10], v[11]);
-            o1.z = act_pack2(out_act, v[12], v[13]); o1.w = act_pack2(out_act, v[14], v[15]);
-            if (warp * 32 + lane < rows_valid) {
-                __half* dst = outputs + (row0 + warp * 32 + lane) * 16;
-                st_stream_u4(dst, o0);
-                st_stream_u4(dst + 8, o1);
-            }
-        }
-        tc::tc_fence_before_sync();
-        __syncthreads();
-    }
-
-    tc::tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc<TM_COLS>(tmem_base);
-}
-
-
-// ==================================================================================================== pipelined kernel
-// mlp_pipe_kernel: the same network, organised so that nothing waits for anything it does not depend on.
+// ==================================================================================================== the kernel
+// mlp_pipe_kernel: organised so that nothing waits for anything it does not depend on.
 //   * input tiles arrive through a TMA ring (cp.async.bulk.tensor, one producer lane): in_dim/8 box loads of [128 rows x 16 B]
 //     land a tile in "chunk-major" order, byte(r,k) = (k/8)*2048 + r*16 + (k%8)*2 — a no-swizzle K-major UMMA operand with
 //     LBO = 2048 (K-adjacent core matrices) and SBO = 128 (M-adjacent); rows past B are zero-filled by the TMA unit;
@@ -401,34 +258,6 @@ static int launch_mlp_pipe(const __half* in, const __half* w, __half* out, __hal
     return check_launch("ffmlp_forward");
 }
 
-template <int WIDTH, bool TRAIN>
-static int launch_mlp(const __half* in, const __half* w, __half* out, __half* fwd, uint32_t B, uint32_t in_dim, uint32_t num_layers, uint32_t act,
-                      uint32_t out_act, cudaStream_t st) {
-    const MlpSmemPlan plan = mlp_smem_plan(in_dim, WIDTH, num_layers);
-    NTX_REQUIRE(plan.total <= 227u * 1024u, NTX_ERR_UNSUPPORTED,
-                "FullyFusedMLP: %u bytes of shared memory needed (hidden=%d, input_dim=%u, num_layers=%u) exceed the 227 KB of a B200 SM", plan.total,
-                WIDTH, in_dim, num_layers);
-    auto kern = mlp_fused_kernel<WIDTH, TRAIN>;
-    static int configured_dev[kMaxDevices] = {};
-    int& configured_smem = configured_dev[current_device()];
-    int occ = 1;
-    if ((int)plan.total > configured_smem) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess) {
-            cudaGetLastError();
-            set_error("FullyFusedMLP: insufficient shared memory available on the GPU.");
-            return NTX_ERR_CUDA;
-        }
-        configured_smem = (int)plan.total;
-    }
-    constexpr int TM_COLS = WIDTH < 32 ? 32 : WIDTH;
-    occ = resident_ctas_per_sm((const void*)kern, kMlpThreads, plan.total, TM_COLS);
-    const int sms = device_sm_count();
-    const uint32_t ntiles = ceil_div<uint32_t>(B, kTileRows);
-    const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)(occ * sms));
-    kern<<<grid, kMlpThreads, plan.total, st>>>(in, w, out, fwd, B, in_dim, num_layers, act, out_act);
-    return check_launch("ffmlp_forward");
-}
-
 static int mlp_forward_dispatch(const void* inputs, const void* weights, uint32_t B, uint32_t input_dim, uint32_t output_dim, uint32_t hidden_dim,
                                 uint32_t num_layers, uint32_t activation, uint32_t output_activation, void* forward_buffer, void* outputs, bool train,
                                 ntx_stream_t stream) {
@@ -447,11 +276,8 @@ static int mlp_forward_dispatch(const void* inputs, const void* weights, uint32_
     auto w = static_cast<const __half*>(weights);
     auto out = static_cast<__half*>(outputs);
     auto fwd = static_cast<__half*>(forward_buffer);
-#define NTX_MLP(WD)                                                                                                             \
-    if (tunables().mlp_impl == 1)                                                                                               \
-        return train ? launch_mlp<WD, true>(in, w, out, fwd, B, input_dim, num_layers, activation, output_activation, st)       \
-                     : launch_mlp<WD, false>(in, w, out, nullptr, B, input_dim, num_layers, activation, output_activation, st); \
-    return train ? launch_mlp_pipe<WD, true>(in, w, out, fwd, B, input_dim, num_layers, activation, output_activation, st)      \
+#define NTX_MLP(WD)                                                                                                        \
+    return train ? launch_mlp_pipe<WD, true>(in, w, out, fwd, B, input_dim, num_layers, activation, output_activation, st) \
                  : launch_mlp_pipe<WD, false>(in, w, out, nullptr, B, input_dim, num_layers, activation, output_activation, st)
     switch (hidden_dim) {
         case 16: NTX_MLP(16);

@@ -306,6 +306,49 @@ __device__ __forceinline__ bool maybe_occupied_ahead(const Ray& r, const MarchPa
     return false;
 }
 
+// The ray parameter beyond which the marcher can no longer probe an occupied voxel (same sampling and the same conservativeness
+// argument as maybe_occupied_ahead: the dilated mip is tested at points half a coarse cell apart, so if neither of two consecutive
+// points is set there is no occupied voxel between them), or -1 if there is none on [t, far) at all.  Evaluated ONCE per ray and
+// frame (frame_init_kernel): every lane of a warp runs the same loop, instead of the marcher interrupting its walk for a scan
+// whenever one of its 32 rays is due for one.
+__device__ __forceinline__ float last_maybe_occupied(const Ray& r, const MarchParams& p, const uint8_t* __restrict__ mip, float t, const float far) {
+    const uint8_t* __restrict__ coarse = mip + kMipHeaderBytes;
+    const uint32_t Hc = p.H >> kMipShift, n = Hc * Hc * Hc;
+    const float inv_speed = 1.0f / fmaxf(fmaxf(fabsf(r.dx), fabsf(r.dy)), fmaxf(fabsf(r.dz), 1e-20f));
+    float last = -1.0f;
+    if (p.C == 1) {
+        const float mb = p.mb0, s = 0.5f * (float)Hc / mb, top = (float)(Hc - 1);
+        const float ax = (r.ox + mb) * s, ay = (r.oy + mb) * s, az = (r.oz + mb) * s, bx = r.dx * s, by = r.dy * s, bz = r.dz * s;
+        const float dt = ((float)kMipCell * mb / (float)p.H) * inv_speed;
+        while (t < far) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float tj = t + (float)j * dt;
+                const int cx = (int)clampf(ax + tj * bx, 0.0f, top), cy = (int)clampf(ay + tj * by, 0.0f, top), cz = (int)clampf(az + tj * bz, 0.0f, top);
+                const uint32_t idx = morton3D_1(cx, cy, cz);
+                if (tj < far && (coarse[idx >> 3] & (1u << (idx & 7u)))) last = tj + dt;
+            }
+            t += 4.0f * dt;
+        }
+        return last;
+    }
+    while (t < far) {
+        const float x = r.ox + t * r.dx, y = r.oy + t * r.dy, z = r.oz + t * r.dz;
+        const int lp = mip_from_pos(clampf(x, -p.bound, p.bound), clampf(y, -p.bound, p.bound), clampf(z, -p.bound, p.bound), p.C);
+        const float step = ((float)kMipCell * fminf((float)(1 << lp), p.bound) / (float)p.H) * inv_speed;
+        for (uint32_t k = 0; k < p.C; k++) {
+            const float mb = fminf((float)(1 << k), p.bound), s = 0.5f * (float)Hc / mb;
+            const int cx = min(max((int)floorf((clampf(x, -mb, mb) + mb) * s), 0), (int)Hc - 1);
+            const int cy = min(max((int)floorf((clampf(y, -mb, mb) + mb) * s), 0), (int)Hc - 1);
+            const int cz = min(max((int)floorf((clampf(z, -mb, mb) + mb) * s), 0), (int)Hc - 1);
+            const uint32_t idx = k * n + morton3D_1(cx, cy, cz);
+            if (coarse[idx >> 3] & (1u << (idx & 7u))) last = t + step;
+        }
+        t += step;
+    }
+    return last;
+}
+
 // ---------------------------------------------------------------------------------------------------- ordered grid-wide scan
 // Workspace layout: u32 ticket, u32 done, then one u64 status word per block:
 //   bits 63..62: 0 = nothing yet, 1 = block aggregate, 2 = inclusive prefix;  bits 61..0: value.
@@ -860,6 +903,142 @@ __global__ void __launch_bounds__(kMarchThreads, 6) march_rays_staged_kernel(
     }
 }
 
+// ---------------------------------------------------------------------------------------------------- compact marcher
+// The marcher of the device-driven frame (ntx_render_rays).  Same walk as march_rays_staged_kernel — same probes in the same order,
+// same float additions, so every sample has bit-identical (t, dt, delta_t) — but a sample leaves the kernel as 12 bytes instead of 32:
+//   ts[row] = the sample's ray parameter t, deltas[row] = (dt, t_end - last_t)        row = ray_slot * n_step + k
+// and the field kernel (MODE_RAYS) rebuilds xyz = clamp(o + t d) itself and reads the view direction from the ray.  With 3 floats
+// per sample a thread keeps a whole speculation window of 8 samples in registers and writes it with six 16-byte stores (a ray's
+// rows are contiguous and 16-byte aligned when n_step % 4 == 0), so the shared-memory staging, its bank conflicts, the block
+// barriers around the copy-out (44 % of the staged kernel's stall samples) and the copy-out itself are gone.
+// live[i] = (row, ray index) of every filled row, appended per block (one block scan + one atomic per launch and block).
+__global__ void __launch_bounds__(kMarchThreads, 6) march_rays_compact_kernel(
+    const int* __restrict__ rays_alive, const float* __restrict__ rays_t, const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float bound,
+    const float dt_gamma, const uint32_t max_steps, const uint32_t C, const uint32_t H, const uint8_t* __restrict__ grid, const float* __restrict__ fars,
+    float* __restrict__ ts, float* __restrict__ deltas, const uint32_t perturb, const uint8_t* __restrict__ coarse, const FrameState* __restrict__ state,
+    unsigned long long* __restrict__ sample_counter, uint32_t walk_budget, int2* __restrict__ live, int* __restrict__ live_counter) {
+    const uint32_t n_alive = (uint32_t)state->n_alive, n_step = (uint32_t)state->n_step;
+    if (state->step == 0 || walk_budget == 0) walk_budget = 0xffffffffu;   // the approach to the object (first iteration) is walked in one go
+    if (blockIdx.x * kMarchThreads >= n_alive) return;
+    const uint32_t n = threadIdx.x + blockIdx.x * kMarchThreads;
+    const bool mine = n < n_alive;
+    const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H, grid);
+    Ray r;
+    float t = 0.f, far = 0.f, last_t = 0.f;
+    int index = 0;
+    if (mine) {
+        index = rays_alive[n];
+        t = rays_t[n];
+        r = load_ray(rays_o + (size_t)index * 3, rays_d + (size_t)index * 3);
+        far = fars[index];
+        if (perturb) {
+            Pcg32 rng; rng.seed((uint64_t)perturb);   // raymarching.cu:1011
+            rng.advance(n);
+            t += p.dt_min * rng.next_float();
+        }
+        if (coarse) {
+            float b_lo, b_hi;
+            if (clip_to_occupied(r, p, coarse, b_lo, b_hi)) far = fminf(far, b_hi); else far = t;
+        }
+        last_t = t;
+    }
+    const size_t row0 = (size_t)n * n_step;
+    float* __restrict__ pl = deltas + row0 * 2;
+    float* __restrict__ pt = ts + row0;
+    const bool vec_ok = (n_step & 3u) == 0;                      // then row0 * 4 bytes is a multiple of 16
+    uint32_t step = 0, empties = 0;                              // step: rows filled so far
+    bool exhausted = !mine, paused = false;
+    while (!exhausted && step < n_step) {
+        // Speculation window (see march_rays_staged_kernel): the next nc lattice samples t, t+dt, ... with all their occupancy loads
+        // in flight at once; the longest all-occupied prefix is accepted, the first empty voxel falls back to the sequential loop.
+        const uint32_t nc = min(kMarchMaxStagedSteps, n_step - step);
+        float tq[kMarchMaxStagedSteps], dq[kMarchMaxStagedSteps], lq[kMarchMaxStagedSteps];
+        uint32_t bitidx[kMarchMaxStagedSteps], byte[kMarchMaxStagedSteps];
+        float tcur = t, x, y, z, dt;
+        uint32_t nspec = 0;
+#pragma unroll
+        for (uint32_t s = 0; s < kMarchMaxStagedSteps; s++) {
+            tq[s] = tcur; dq[s] = 0.f; lq[s] = 0.f; bitidx[s] = 0; byte[s] = 0;
+            if (s < nc && tcur < far) {
+                const uint32_t vox = locate(r, p, tcur, x, y, z, dt);
+                bitidx[s] = vox & 7u;
+                byte[s] = p.grid[vox >> 3];
+                const float t_end = tcur + dt;                   // == the sequential marcher's `t += dt`
+                dq[s] = dt;
+                lq[s] = t_end - (s == 0 ? last_t : tcur);        // last_t of sample s > 0 is the end of sample s-1 = tcur
+                tcur = t_end;
+                nspec = s + 1;
+            }
+        }
+        uint32_t acc = 0;
+        bool run = true;
+#pragma unroll
+        for (uint32_t s = 0; s < kMarchMaxStagedSteps; s++) {
+            if (s < nspec && run) {
+                if (byte[s] & (1u << bitidx[s])) acc = s + 1; else run = false;
+            }
+        }
+        if (acc == kMarchMaxStagedSteps && vec_ok && (step & 3u) == 0) {
+            // a full window: 8 samples = 64 bytes of deltas + 32 bytes of ts, all 16-byte aligned
+            float4* d4 = reinterpret_cast<float4*>(pl + 2 * step);
+            d4[0] = make_float4(dq[0], lq[0], dq[1], lq[1]); d4[1] = make_float4(dq[2], lq[2], dq[3], lq[3]);
+            d4[2] = make_float4(dq[4], lq[4], dq[5], lq[5]); d4[3] = make_float4(dq[6], lq[6], dq[7], lq[7]);
+            float4* t4 = reinterpret_cast<float4*>(pt + step);
+            t4[0] = make_float4(tq[0], tq[1], tq[2], tq[3]); t4[1] = make_float4(tq[4], tq[5], tq[6], tq[7]);
+        } else {
+#pragma unroll
+            for (uint32_t s = 0; s < kMarchMaxStagedSteps; s++)
+                if (s < acc) { pl[2 * (step + s)] = dq[s]; pl[2 * (step + s) + 1] = lq[s]; pt[step + s] = tq[s]; }
+        }
+        if (acc) {
+            // t after the accepted samples: the start of the next speculated one (tq[acc]), or the end of the window
+            float tn = tcur;
+#pragma unroll
+            for (uint32_t s = 1; s < kMarchMaxStagedSteps; s++) if (s == acc) tn = tq[s];
+            t = tn; last_t = tn;
+        }
+        const uint32_t window_end = step + nc;
+        step += acc;
+        while (t < far && step < window_end) {
+            if (probe(r, p, t, x, y, z, dt)) {
+                pt[step] = t;
+                t += dt;
+                pl[2 * step] = dt; pl[2 * step + 1] = t - last_t;
+                last_t = t;
+                step++;
+            } else {
+                // (probe() has advanced t to the next voxel)
+                if (coarse && ((empties & 3u) == 0u)) {
+                    if (!maybe_occupied_ahead(r, p, coarse, t, far)) { far = t; break; }
+                }
+                if (++empties > walk_budget && t < far) { paused = true; break; }
+            }
+        }
+        if (step < window_end) exhausted = true;                 // ran out of ray (or paused): the next slot is the sentinel
+    }
+    if (mine && step < n_step) { pl[2 * step] = 0.f; pl[2 * step + 1] = paused ? -t : 0.f; }   // composite_rays stops at (0, .); (0, -t) = paused at t
+    const uint32_t filled = mine ? step : 0u;
+    {
+        __shared__ uint32_t s_scan[33];
+        __shared__ uint32_t s_base;
+        uint32_t total;
+        const uint32_t excl = block_exclusive_scan(filled, total, s_scan);
+        if (threadIdx.x == 0) s_base = total ? (uint32_t)atomicAdd(live_counter, (int)total) : 0u;
+        __syncthreads();
+        int2* __restrict__ dst = live + s_base + excl;
+        for (uint32_t j = 0; j < filled; j++) dst[j] = make_int2((int)(row0 + j), index);
+    }
+    if (sample_counter && mine) {                                // bench / statistics only: samples emitted in this launch
+        if (__activemask() == 0xffffffffu) {
+            uint32_t cnt = filled;
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(sample_counter, (unsigned long long)cnt);
+        } else {
+            atomicAdd(sample_counter, (unsigned long long)filled);
+        }
+    }
+}
+
 // raymarching.cu:1021-1104
 __global__ void __launch_bounds__(128) composite_rays_kernel(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_alive,
                                                              float* __restrict__ rays_t, const float* __restrict__ sigmas, const float* __restrict__ rgbs,
@@ -912,6 +1091,15 @@ __global__ void __launch_bounds__(128) composite_rays_kernel(uint32_t n_alive, u
     image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
 }
 
+// samples per ray of an iteration of the device-driven frame: the reference's clamp(budget // n_alive, 1, cap) (renderer.py:464 with
+// budget = N, cap = 8).  Wide schedules (cap > 8) round down to a multiple of 4 so that a ray's rows start 16-byte aligned in
+// ts / deltas (vector stores in the marcher, vector loads in composite_rays); the image does not depend on n_step.
+__device__ __forceinline__ uint32_t schedule_n_step(uint32_t budget, uint32_t n_alive, uint32_t cap) {
+    uint32_t n = max(min(budget / n_alive, cap), 1u);
+    if (cap > 8u && n >= 4u) n &= ~3u;
+    return n;
+}
+
 // ordered stream compaction (raymarching.cu:1117-1134, atomics replaced by scans)
 constexpr int kCompactThreads = 256;
 constexpr int kCompactItems = 4;
@@ -953,7 +1141,7 @@ __global__ void __launch_bounds__(kCompactThreads) compact_rays_kernel(uint32_t 
             FrameState s;
             s.step = state_in->step + state_in->n_step;                       // step += n_step   (renderer.py:475)
             s.n_alive = ((uint32_t)s.step < max_steps) ? (int)total : 0;       // while step < max_steps
-            s.n_step = s.n_alive ? (int)max(min(budget / (uint32_t)s.n_alive, max_n_step), 1u) : 0;   // renderer.py:464 with (N, 8)
+            s.n_step = s.n_alive ? (int)schedule_n_step(budget, (uint32_t)s.n_alive, max_n_step) : 0;
             const uint32_t m = (uint32_t)s.n_alive * (uint32_t)s.n_step;
             s.m_padded = s.n_alive ? (int)(m + 128u - (m % 128u)) : 0;         // raymarching.py:386-387 (align = 128)
             s.n_live = 0; s.pad0 = s.pad1 = s.pad2 = 0;
@@ -1182,26 +1370,51 @@ extern "C" int ntx_compact_rays(uint32_t n_alive, int* rays_alive, const int* ra
 
 // ---------------------------------------------------------------------------------------------------- device-driven frame
 namespace ntx {
+// rays_alive = 0..N-1, rays_t = nears (renderer.py:449-451).  With `prekill` (schedules other than the reference's) the occupancy
+// mip is consulted ONCE per ray here instead of inside the marcher's walk: a ray that cannot reach anything occupied starts dead
+// (rays_t = -1: it could not emit a sample; the reference finds that out by marching it through the cube and drops it in its first
+// composite_rays with nothing accumulated — same image), and the others get `far` shortened to the end of their last maybe-occupied
+// stretch, beyond which the marcher would only cross empty voxels and die.  The marcher then runs without any mip test in its loop:
+// with 32 rays per warp whose tests fell due at different iterations, almost every iteration of every warp used to pay for a scan
+// (first launch 485 us).  The compaction that follows is the ordinary compact_rays_kernel.
 __global__ void __launch_bounds__(256) frame_init_kernel(const uint32_t N, const uint32_t budget, const uint32_t max_n_step, const float* __restrict__ nears,
-                                                         int* __restrict__ rays_alive, float* __restrict__ rays_t, FrameState* __restrict__ state,
-                                                         volatile int* host_mailbox) {
+                                                         float* __restrict__ fars, int* __restrict__ rays_alive, float* __restrict__ rays_t,
+                                                         FrameState* __restrict__ state, volatile int* host_mailbox, const bool prekill, const float* __restrict__ rays_o,
+                                                         const float* __restrict__ rays_d, const float bound, const float dt_gamma, const uint32_t max_steps,
+                                                         const uint32_t C, const uint32_t H, const uint8_t* __restrict__ coarse) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n < N) { rays_alive[n] = (int)n; rays_t[n] = nears[n]; }       // renderer.py:449-451
+    if (n < N) {
+        float t = nears[n];
+        if (prekill) {
+            const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H, nullptr);
+            const Ray r = load_ray(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
+            float b_lo, b_hi;
+            if (!clip_to_occupied(r, p, coarse, b_lo, b_hi)) t = -1.0f;
+            else {
+                // the end of the ray's useful part, once: beyond it the marcher could only walk empty voxels and die
+                const float far0 = fminf(fars[n], b_hi);
+                const float t_end = last_maybe_occupied(r, p, coarse, fmaxf(t, b_lo), far0);
+                if (t_end < 0.0f) t = -1.0f; else fars[n] = fminf(far0, t_end);
+            }
+        }
+        rays_alive[n] = (int)n; rays_t[n] = t;
+    }
     if (n == 0) {
         FrameState s;
-        s.step = 0; s.n_alive = (int)N; s.n_step = (int)max(min(budget / N, max_n_step), 1u);   // N // N = 1 for the reference schedule
+        s.step = 0; s.n_alive = (int)N;
+        s.n_step = prekill ? 0 : (int)schedule_n_step(budget, N, max_n_step);   // prekill: a compaction follows and plans iteration 0 (step += 0)
         const uint32_t m = N * (uint32_t)s.n_step;
         s.m_padded = (int)(m + 128u - (m % 128u));
         s.n_live = 0; s.pad0 = s.pad1 = s.pad2 = 0;
         *state = s;
-        if (host_mailbox) { *host_mailbox = (int)N; __threadfence_system(); }
+        if (host_mailbox && !prekill) { *host_mailbox = (int)N; __threadfence_system(); }
     }
 }
 
 struct FrameWorkspace {
-    float *nears, *fars, *rays_t[2], *xyzs, *dirs, *deltas, *sigmas, *rgbs;
+    float *nears, *fars, *rays_t[2], *ts, *deltas, *sigmas, *rgbs;
     int* rays_alive[2];
-    int* live_rows;
+    int2* live;            // (row, ray) of every row the marcher filled this iteration
     FrameState* state;     // [2]
     ScanWS* scan;
     size_t bytes;
@@ -1216,12 +1429,11 @@ static FrameWorkspace carve_frame_workspace(void* base, uint32_t N, uint32_t bud
     w.nears = static_cast<float*>(take(sizeof(float) * N));
     w.fars = static_cast<float*>(take(sizeof(float) * N));
     for (int i = 0; i < 2; i++) { w.rays_alive[i] = static_cast<int*>(take(sizeof(int) * N)); w.rays_t[i] = static_cast<float*>(take(sizeof(float) * N)); }
-    w.xyzs = static_cast<float*>(take(sizeof(float) * 3 * Mmax));
-    w.dirs = static_cast<float*>(take(sizeof(float) * 3 * Mmax));
+    w.ts = static_cast<float*>(take(sizeof(float) * Mmax));
     w.deltas = static_cast<float*>(take(sizeof(float) * 2 * Mmax));
     w.sigmas = static_cast<float*>(take(sizeof(float) * Mmax));
     w.rgbs = static_cast<float*>(take(sizeof(float) * 3 * Mmax));
-    w.live_rows = static_cast<int*>(take(sizeof(int) * Mmax));
+    w.live = static_cast<int2*>(take(sizeof(int2) * Mmax));
     w.bytes = off;
     return w;
 }
@@ -1230,6 +1442,8 @@ static FrameWorkspace carve_frame_workspace(void* base, uint32_t N, uint32_t bud
 extern "C" size_t ntx_render_rays_workspace_bytes(uint32_t N, uint32_t sample_budget) {
     return carve_frame_workspace(nullptr, N, sample_budget ? sample_budget : N).bytes;
 }
+
+#include <mutex>
 
 extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const float* aabb, float min_near, float bound, float dt_gamma,
                                uint32_t max_steps, uint32_t perturb, uint32_t sample_budget, uint32_t max_n_step, uint32_t walk_budget, uint32_t C, uint32_t H,
@@ -1252,7 +1466,10 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
     NTX_REQUIRE(max_n_step <= 1024 && (uint64_t)max(N, sample_budget) + 128 < (1ull << 31), NTX_ERR_INVALID_ARGUMENT, "render_rays: bad sample_budget / max_n_step");
     cudaStream_t st = ST(stream);
     const FrameWorkspace w = carve_frame_workspace(workspace, N, sample_budget);
-    // events that bound how far the launching thread runs ahead of the device (one set per device; the call is not re-entrant)
+    // One frame at a time per device: the run-ahead events (and the optional profiling events) below are per-device state, so
+    // concurrent calls from several threads on one device take turns here; calls on different devices do not interact.
+    static std::mutex frame_mutex[kMaxDevices];
+    std::lock_guard<std::mutex> frame_lock(frame_mutex[current_device()]);
     constexpr int kEvents = 4;
     static cudaEvent_t ev_dev[kMaxDevices][kEvents];
     static bool ev_ready_dev[kMaxDevices] = {};
@@ -1269,18 +1486,16 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
     cudaMemsetAsync(depth, 0, sizeof(float) * N, st);
     cudaMemsetAsync(image, 0, sizeof(float) * 3 * N, st);
     near_far_kernel<<<ceil_div<uint32_t>(N, 128), 128, 0, st>>>(rays_o, rays_d, aabb, N, min_near, w.nears, w.fars);
-    static bool smem_ready_dev[kMaxDevices] = {};
-    bool& smem_ready = smem_ready_dev[current_device()];
-    const size_t march_smem = (size_t)kMarchThreads * kMarchMaxStagedSteps * 8 * sizeof(float);
-    if (!smem_ready) {
-        cudaFuncSetAttribute(march_rays_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march_smem);
-        smem_ready = true;
-    }
     // Loop bounds.  Without pauses every iteration gives each living ray n_step samples, and `step` (their sum) reaching max_steps
     // ends the loop like the reference's `while step < max_steps`.  A paused ray spends iterations without sampling — at most
     // (voxels on a ray) / walk_budget < 2*H*C / walk_budget of them — so the bounds grow by that much; rays still end at t >= far.
+    // (With pauses a ray that never pauses may therefore take up to step_limit > max_steps samples where the reference truncates at
+    // max_steps: only reachable when a ray crosses more than max_steps occupied lattice points, i.e. not with dt_gamma = 0 and
+    // max_steps >= 2*sqrt(3)*bound/dt_min; use walk_budget = 0 where that cap matters.)
     const uint32_t pause_iters = walk_budget ? 2u * H * C / walk_budget + 2u : 0u;
     const uint32_t step_limit = max_steps + pause_iters * max_n_step, iter_limit = max_steps + pause_iters;
+    // rays that cannot hit anything occupied start dead (see frame_init_kernel); not for the reference's exact iteration structure
+    const bool prekill = walk_budget != 0 && occupancy_mip != nullptr;
     uint32_t bound_rays = N, iterations = 0, kernels = 1;   // near_far
     // optional per-kernel timing (bench.py's roofline): CUDA events around every march and field launch of this frame
     constexpr uint32_t kProfIters = 256;
@@ -1300,28 +1515,34 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
         const int cur = i & 1, old = cur ^ 1;
         FrameState* s_cur = w.state + cur;
         if (i == 0) {
-            frame_init_kernel<<<ceil_div<uint32_t>(N, 256), 256, 0, st>>>(N, sample_budget, max_n_step, w.nears, w.rays_alive[0], w.rays_t[0], s_cur, host_mailbox);
-        } else {
+            // without prekill the initial state IS iteration 0's; with it, iteration 0 starts with a compaction like every other one
+            frame_init_kernel<<<ceil_div<uint32_t>(N, 256), 256, 0, st>>>(N, sample_budget, max_n_step, w.nears, w.fars, w.rays_alive[prekill ? old : cur],
+                                                                          w.rays_t[prekill ? old : cur], prekill ? w.state + old : s_cur, host_mailbox, prekill,
+                                                                          rays_o, rays_d, bound, dt_gamma, max_steps, C, H, occupancy_mip);
+            kernels += 1;
+        }
+        if (i > 0 || prekill) {
             compact_rays_kernel<<<ceil_div<uint32_t>(bound_rays, kCompactThreads * kCompactItems), kCompactThreads, 0, st>>>(
                 bound_rays, w.rays_alive[cur], w.rays_alive[old], w.rays_t[cur], w.rays_t[old], nullptr, w.scan, w.state + old, s_cur, sample_budget, max_n_step, step_limit,
                 host_mailbox + i);
+            kernels += 1;
         }
         const bool timed = prof && i < kProfIters;
         if (timed) { cudaEventRecord(prof[3 * i], st); prof_iters = i + 1; }
-        // padding rows (at most 128) are cleared by the first threads of the launch: at least one block
-        march_rays_staged_kernel<<<ceil_div<uint32_t>(max(bound_rays, 128u), kMarchThreads), kMarchThreads, march_smem, st>>>(
-            bound_rays, 1, w.rays_alive[cur], w.rays_t[cur], rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, w.nears, w.fars, w.xyzs, w.dirs, w.deltas, perturb, 0,
-            occupancy_mip, s_cur, sample_counter, walk_budget, w.live_rows, &s_cur->n_live);
+        march_rays_compact_kernel<<<ceil_div<uint32_t>(bound_rays, kMarchThreads), kMarchThreads, 0, st>>>(
+            w.rays_alive[cur], w.rays_t[cur], rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, w.fars, w.ts, w.deltas, perturb, prekill ? nullptr : occupancy_mip, s_cur, sample_counter,
+            walk_budget, w.live, &s_cur->n_live);
         const uint32_t m_bound = (uint32_t)min((uint64_t)max(N, sample_budget), (uint64_t)bound_rays * max_n_step) + 128u;
         if (timed) cudaEventRecord(prof[3 * i + 1], st);
-        // the field runs over the list of rows the marcher filled (no tile is spent on sentinel rows)
-        const int rc = launch_ngp_field(w.xyzs, w.dirs, nullptr, m_bound, &s_cur->n_live, w.live_rows, bound, embeddings_f16, offsets, L, S, base_resolution,
-                                        align_corners, w_sigma_f16, w_color_f16, density_scale, w.sigmas, w.rgbs, st);
+        // the field runs over the list of rows the marcher filled (no tile is spent on sentinel rows); positions and view directions
+        // are rebuilt from (ray, t)
+        const int rc = launch_ngp_field_rays(w.live, &s_cur->n_live, m_bound, w.ts, rays_o, rays_d, bound, embeddings_f16, offsets, L, S, base_resolution, align_corners,
+                                             w_sigma_f16, w_color_f16, density_scale, w.sigmas, w.rgbs, st);
         if (rc != NTX_OK) return rc;
         if (timed) cudaEventRecord(prof[3 * i + 2], st);
         composite_rays_kernel<<<ceil_div<uint32_t>(bound_rays, 128), 128, 0, st>>>(bound_rays, 1, w.rays_alive[cur], w.rays_t[cur], w.sigmas, w.rgbs, w.deltas, weights_sum,
                                                                                   depth, image, s_cur);
-        kernels += 4;                                       // init | compact, march, field, composite
+        kernels += 3;                                       // march, field, composite
         cudaEventRecord(ev[i % kEvents], st);
         if (i >= 1) {
             // iteration i-1 has certainly been planned once its event fires; iteration i is queued behind it, so the device
@@ -1344,4 +1565,36 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
         }
     }
     return check_launch("render_rays");
+}
+
+// ---------------------------------------------------------------------------------------------------- sharded frame assembly
+// The N>1 path's epilogue in one kernel ("one exchange step at the end ... followed by a local un-permute"): every rank
+// renders interleaved tiles of `tile` consecutive rays (tile k -> rank k % world) straight into a planar block
+//   [weights_sum (n_max) | depth (n_max) | rgb (3 n_max)]
+// the blocks are all-gathered as they are, and this kernel puts every ray back at its image position and adds the background term
+// image + (1 - weights_sum) * bg (renderer.py:485) on the way.  world = 1 is the single-GPU epilogue (identity permutation).
+namespace ntx {
+__global__ void __launch_bounds__(256) unshard_frame_kernel(const float* __restrict__ gathered, const uint32_t world, const uint32_t n_max, const uint32_t tile,
+                                                            const uint32_t N, const float bg, float* __restrict__ image, float* __restrict__ depth,
+                                                            float* __restrict__ weights_sum) {
+    const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= N) return;
+    const uint32_t k = ray / tile, rank = k % world, j = (k / world) * tile + (ray - k * tile);
+    const float* blk = gathered + (size_t)rank * 5u * n_max;
+    const float ws = blk[j];
+    weights_sum[ray] = ws;
+    depth[ray] = blk[n_max + j];
+    const float b = __fmul_rn(__fsub_rn(1.0f, ws), bg);       // one rounding per torch op of `image + (1 - weights_sum).unsqueeze(-1) * bg_color`: no FMA
+    const float* c = blk + 2u * (size_t)n_max + 3u * (size_t)j;
+    image[(size_t)ray * 3] = __fadd_rn(c[0], b); image[(size_t)ray * 3 + 1] = __fadd_rn(c[1], b); image[(size_t)ray * 3 + 2] = __fadd_rn(c[2], b);
+}
+}  // namespace ntx
+
+extern "C" int ntx_unshard_frame(const float* gathered, uint32_t world, uint32_t n_max, uint32_t tile, uint32_t N, float bg, float* image, float* depth,
+                                 float* weights_sum, ntx_stream_t stream) {
+    NTX_REQUIRE(gathered && image && depth && weights_sum, NTX_ERR_INVALID_ARGUMENT, "unshard_frame: null pointer");
+    NTX_REQUIRE(world >= 1 && tile >= 1 && n_max >= 1, NTX_ERR_INVALID_ARGUMENT, "unshard_frame: bad world / tile / n_max");
+    if (N == 0) return NTX_OK;
+    unshard_frame_kernel<<<ceil_div<uint32_t>(N, 256), 256, 0, ST(stream)>>>(gathered, world, n_max, tile, N, bg, image, depth, weights_sum);
+    return check_launch("unshard_frame");
 }

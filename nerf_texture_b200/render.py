@@ -122,7 +122,7 @@ def _aabb_tensor(bound, dev, cache={}):
 
 
 def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aabb=None, min_near=0.2, dt_gamma=0.0, max_steps=1024, bg_color=1.0,
-                perturb=0, count_samples=False, profile=None, use_mip=True, device_loop=True, mip=None, schedule="auto", time_kernels=False):
+                perturb=0, count_samples=False, profile=None, use_mip=True, device_loop=True, mip=None, schedule="auto", time_kernels=False, block_rows=None):
     """Inference branch of NeRFRenderer.run_cuda (renderer.py:436-489).  rays_o/d [N,3] fp32 CUDA.
     Returns dict(image [N,3], depth [N], weights_sum [N], iterations, n_samples (if count_samples)).
     device_loop=True (default): the whole loop is ONE libntx call whose iteration state stays on the device (ntx_render_rays);
@@ -132,7 +132,9 @@ def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aab
     time_kernels (device loop only): also return march_ms / field_ms, the summed CUDA-event times of the frame's march and field launches.
     mip: optional pre-built occupancy mip (ntx_build_occupancy_mip) of density_bitfield.
     schedule (device loop only): "auto" (auto_schedule(N); the reference's when perturb != 0), "reference", "wide", or a
-    (budget_multiple, max_n_step) pair — the image is the same either way, see include/ntx.h."""
+    (budget_multiple, max_n_step) pair — the image is the same either way, see include/ntx.h.
+    block_rows (device loop only, used by the sharded path): return the raw planar result block [weights_sum | depth | rgb] padded to
+    block_rows rays per plane (no background term yet) instead of the finished image."""
     dev = rays_o.device
     rays_o = rays_o.contiguous().view(-1, 3).float()
     rays_d = rays_d.contiguous().view(-1, 3).float()
@@ -154,9 +156,11 @@ def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aab
         mult, cap = SCHEDULES[schedule] if isinstance(schedule, str) else schedule
         budget = int(mult) * N
         ws, ws_ptr, mailbox, counter = _frame_buffers(dev, N, int(max_steps), budget, int(max_steps) + 2 * int(grid_size) * int(cascade) + 8)
-        image_c = torch.empty(N, 3, dtype=torch.float32, device=dev)
-        depth_c = torch.empty(N, dtype=torch.float32, device=dev)
-        wsum_c = torch.empty(N, dtype=torch.float32, device=dev)
+        # the raw result as ONE planar block [weights_sum (n) | depth (n) | rgb (3n)]: what a rank sends in the sharded path, and what
+        # the fused epilogue (ntx_unshard_frame: un-permute + background term) reads
+        n_blk = N if block_rows is None else int(block_rows)
+        block = torch.empty(5 * n_blk, dtype=torch.float32, device=dev)
+        wsum_c, depth_c, image_c = block[:N], block[n_blk:n_blk + N], block[2 * n_blk:2 * n_blk + 3 * N].view(N, 3)
         if count_samples:
             counter.zero_()
         stats = (ctypes.c_uint32 * 2)()
@@ -167,8 +171,16 @@ def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aab
                L.ptr(wsum_c), L.ptr(depth_c), L.ptr(image_c), ws_ptr, mailbox.data_ptr(), counter.data_ptr() if count_samples else None,
                ctypes.addressof(stats), ctypes.addressof(kms) if time_kernels else None, st)
         L.launches += int(stats[1]) - 1          # L.call counted the call as one launch
-        image = image_c + (1 - wsum_c).unsqueeze(-1) * bg_color
-        out = dict(image=image, depth=depth_c, weights_sum=wsum_c, iterations=int(stats[0]))
+        if block_rows is not None:               # sharded frame: the caller all-gathers the block and assembles the image
+            out = dict(block=block, iterations=int(stats[0]))
+        elif isinstance(bg_color, (int, float)):
+            image = torch.empty(N, 3, dtype=torch.float32, device=dev)
+            depth = torch.empty(N, dtype=torch.float32, device=dev)
+            wsum = torch.empty(N, dtype=torch.float32, device=dev)
+            L.call("ntx_unshard_frame", L.ptr(block), 1, N, max(N, 1), N, float(bg_color), L.ptr(image), L.ptr(depth), L.ptr(wsum), st)   # image + (1 - weights_sum) * bg
+            out = dict(image=image, depth=depth, weights_sum=wsum, iterations=int(stats[0]))
+        else:                                    # per-ray background tensor (renderer.py:354-355)
+            out = dict(image=image_c + (1 - wsum_c).unsqueeze(-1) * bg_color, depth=depth_c, weights_sum=wsum_c, iterations=int(stats[0]))
         if count_samples:
             out["n_samples"] = int(counter.item())
         if time_kernels:
@@ -261,34 +273,50 @@ def _shard_plan(N, world, tile, device):
     return plan
 
 
-def gather_frame(out, N, group=None, tile=1024):
-    """ONE all_gather of the packed per-rank result (rgb, depth, alpha = 20 B/ray) + un-permute to image order."""
+def gather_frame(out, N, group=None, tile=1024, bg_color=1.0):
+    """ONE all_gather of the per-rank planar result blocks (weights_sum | depth | rgb = 20 B/ray) + one kernel that puts every ray
+    back at its image position and adds the background term (ntx_unshard_frame).
+    out: render_rays(..., block_rows=n_max) (raw block, background added here) or a finished per-rank result dict (packed here)."""
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    dev = out["image"].device
-    idxs, n_max, inv = _shard_plan(N, world, tile, dev)
-    n_local = idxs[rank].numel()
-    packed = torch.empty(n_max, 5, dtype=torch.float32, device=dev)
-    packed[:n_local, 0:3] = out["image"]
-    packed[:n_local, 3] = out["depth"]
-    packed[:n_local, 4] = out["weights_sum"]
-    gathered = torch.empty(world * n_max, 5, dtype=torch.float32, device=dev)
-    dist.all_gather_into_tensor(gathered, packed, group=group)        # the path's only collective (NCCL over NVLink)
-    full = gathered[inv]
-    res = dict(image=full[:, 0:3], depth=full[:, 3], weights_sum=full[:, 4], iterations=out["iterations"])
+    idxs, n_max, _ = _shard_plan(N, world, tile, torch.device("cpu"))
+    if "block" in out:
+        block = out["block"]                                            # rendered straight into the send layout
+    else:                                                               # finished result (its image already holds the background term)
+        n_local = idxs[rank].numel()
+        block = torch.zeros(5 * n_max, dtype=torch.float32, device=out["image"].device)
+        block[:n_local] = out["weights_sum"]
+        block[n_max:n_max + n_local] = out["depth"]
+        block[2 * n_max:2 * n_max + 3 * n_local] = out["image"].reshape(-1)
+        bg_color = 0.0
+    dev = block.device
+    gathered = torch.empty(world * 5 * n_max, dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(gathered, block, group=group)           # the path's only collective (NCCL over NVLink)
+    if dev.type == "cuda":
+        image = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        depth = torch.empty(N, dtype=torch.float32, device=dev)
+        wsum = torch.empty(N, dtype=torch.float32, device=dev)
+        L.call("ntx_unshard_frame", L.ptr(gathered), world, n_max, tile, N, float(bg_color), L.ptr(image), L.ptr(depth), L.ptr(wsum), L.stream())
+    else:                                                               # the same index rule on the host (gloo tests)
+        ray = torch.arange(N)
+        k = ray // tile
+        base, j = (k % world) * 5 * n_max, (k // world) * tile + ray % tile
+        wsum, depth = gathered[base + j], gathered[base + n_max + j]
+        image = gathered[(base + 2 * n_max + 3 * j)[:, None] + torch.arange(3)[None, :]] + ((1 - wsum) * float(bg_color))[:, None]
+    res = dict(image=image, depth=depth, weights_sum=wsum, iterations=out["iterations"])
     if "n_samples" in out:
         res["n_samples"] = out["n_samples"]
     return res
 
 
-def render_image_sharded(field, rays_o, rays_d, density_bitfield, cascade, grid_size, group=None, tile=1024, **kw):
-    """Each rank renders its interleaved tiles of the frame; ONE all_gather of the packed (rgb, depth, alpha) rows follows.
-    rays_o/rays_d: the full frame's rays on every rank ([N,3], e.g. generated on-device from the pose)."""
+def render_image_sharded(field, rays_o, rays_d, density_bitfield, cascade, grid_size, group=None, tile=1024, bg_color=1.0, **kw):
+    """Each rank renders its interleaved tiles of the frame straight into its planar send block; ONE all_gather and one assembly
+    kernel follow.  rays_o/rays_d: the full frame's rays on every rank ([N,3], e.g. generated on-device from the pose)."""
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, **kw)
+        return render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, bg_color=bg_color, **kw)
     N = rays_o.shape[0]
-    idxs, _, _ = _shard_plan(N, dist.get_world_size(group), tile, rays_o.device)
+    idxs, n_max, _ = _shard_plan(N, dist.get_world_size(group), tile, rays_o.device)
     idx = idxs[dist.get_rank(group)]
-    out = render_rays(field, rays_o[idx], rays_d[idx], density_bitfield, cascade, grid_size, **kw)
-    return gather_frame(out, N, group, tile)
+    out = render_rays(field, rays_o[idx], rays_d[idx], density_bitfield, cascade, grid_size, block_rows=n_max, **kw)
+    return gather_frame(out, N, group, tile, bg_color=bg_color)

@@ -18,8 +18,8 @@ REF_CUDA = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "_ref_raymarching
     os.path.join(ROOT, "baseline", "_ref", "wrappers", "gridencoder", "grid.py"))
 
 
-def _run(backend, size, out):
-    r = subprocess.run([sys.executable, TOOL, "--backend", backend, "--size", str(size), "--out", out], capture_output=True, text=True, timeout=900)
+def _run(backend, size, out, *extra):
+    r = subprocess.run([sys.executable, TOOL, "--backend", backend, "--size", str(size), "--out", out] + list(extra), capture_output=True, text=True, timeout=900)
     line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
     assert line, "run_reference_files.py --backend %s failed:\n%s\n%s" % (backend, r.stdout[-2000:], r.stderr[-4000:])
     return json.loads(line[0][7:]), np.load(out)
@@ -50,7 +50,8 @@ def test_unmodified_renderer_on_libntx_matches_reference_stack(tmp_path):
     assert 0.05 < hit.mean() < 0.6
     if not REF_CUDA:
         pytest.skip("oracle/_ref (reference CUDA) not built: product arm checked alone")
-    info_r, img_r = _run("ref", 256, str(tmp_path / "ref.npz"))
+    ckpt = str(tmp_path / "reference_stack.pth")
+    info_r, img_r = _run("ref", 256, str(tmp_path / "ref.npz"), "--save-ckpt", ckpt)
     assert "baseline/_ref/wrappers" in info_r["raymarching"].replace("\\", "/")
     assert info_n["iterations"] == info_r["iterations"], (info_n, info_r)          # the reference's own loop structure (n_step = N // n_alive ...)
     assert info_n["samples"] == info_r["samples"], (info_n, info_r)                # same samples marched (integer, exact)
@@ -59,3 +60,9 @@ def test_unmodified_renderer_on_libntx_matches_reference_stack(tmp_path):
     # tolerance: north_star's 1e-4 on the composited fp32 image (fp16 MLP outputs differ by ulps between fp32 and fp16 accumulation)
     assert d_img.max() <= 1e-4, "image differs from the reference stack: max %g mean %g" % (d_img.max(), d_img.mean())
     assert d_dep.max() <= 1e-4 * max(1.0, float(np.abs(img_r["depth"]).max())), "depth differs: max %g" % d_dep.max()
+    # checkpoint round trip: the .pth the REFERENCE stack's model wrote loads into the drop-in modules (strict key / shape
+    # match, Trainer.load_checkpoint's code path) and renders the same frame
+    info_c, img_c = _run("ntx", 256, str(tmp_path / "ntx_ckpt.npz"), "--load-ckpt", ckpt)
+    assert info_c["iterations"] == info_r["iterations"] and info_c["samples"] == info_r["samples"]
+    np.testing.assert_array_equal(img_c["image"], img_n["image"])          # same parameters as the seeded build, bit for bit
+    assert np.abs(img_c["image"] - img_r["image"]).max() <= 1e-4

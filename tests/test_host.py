@@ -138,3 +138,63 @@ def test_level_offsets_match_the_oracle_and_the_reference_rule():
         got = hashgrid_level_offsets(cfg["input_dim"], cfg["num_levels"], enc.per_level_scale, cfg["base_resolution"], cfg["log2_hashmap_size"], cfg["align_corners"])
         assert got == enc.offsets.tolist() and all(n % 8 == 0 for n in np.diff(got))
         assert enc.embeddings.shape == (got[-1], cfg["level_dim"]) and enc.output_dim == cfg["num_levels"] * cfg["level_dim"]
+
+
+DP_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from nerf_texture_b200 import parallel
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=2)
+rank = dist.get_rank()
+g = torch.Generator().manual_seed(7)
+shapes = [(1000, 2), (64 * 112,), (64 * 176,)]          # table slice, sigma-net weights, colour-net weights
+full = [[torch.randn(*s, generator=g) for s in shapes] for _ in range(2)]     # the gradients of rank 0 and rank 1
+params = [torch.nn.Parameter(torch.zeros(*s)) for s in shapes]
+for p, gr in zip(params, full[rank]):
+    p.grad = gr.clone()
+params[1].grad = None if rank == 1 else params[1].grad               # a rank without a gradient for one parameter contributes zeros
+parallel.allreduce_gradients(params, average=True)
+want = [(full[0][i] + (full[1][i] if i != 1 else 0)) / 2 for i in range(3)]
+ok = all(torch.allclose(p.grad, w, rtol=0, atol=1e-6) for p, w in zip(params, want))
+print("RANK%%d %%s" %% (rank, "OK" if ok else "MISMATCH"))
+dist.destroy_process_group()
+""" % ROOT
+
+
+def test_two_rank_gradient_allreduce_gloo():
+    """the data-parallel step's one collective — all gradients packed into one buffer, summed over the ranks, averaged"""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29519", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, "-c", DP_WORKER], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120) for p in procs]
+    for r, (so, se) in enumerate(outs):
+        assert "RANK%d OK" % r in so, (so, se[-2000:])
+
+
+def test_checkpoint_round_trip_cpu(tmp_path):
+    """the state a reference Trainer checkpoint holds for the hot path (nerf/utils.py:1490-1521: {'model': state_dict, ...}) survives
+    torch.save / torch.load / load_state_dict(strict=True) on the drop-in modules, with the reference's parameter names and shapes"""
+    _compat()
+    from ffmlp import FFMLP
+    from gridencoder import GridEncoder
+
+    class Field(torch.nn.Module):           # the attribute names of nerf/network_ff.py:29-49
+        def __init__(self):
+            super().__init__()
+            self.encoder = GridEncoder(input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=15, desired_resolution=512, align_corners=True)
+            self.sigma_net = FFMLP(input_dim=32, output_dim=16, hidden_dim=64, num_layers=2)
+            self.color_net = FFMLP(input_dim=32, output_dim=3, hidden_dim=64, num_layers=3)
+
+    a, b = Field(), Field()
+    with torch.no_grad():
+        a.encoder.embeddings.uniform_(-1, 1)
+        a.sigma_net.weights.uniform_(-1, 1)
+    sd = a.state_dict()
+    assert set(sd) == {"encoder.embeddings", "encoder.offsets", "sigma_net.weights", "color_net.weights"}      # grid.py:125-131, ffmlp.py:136
+    assert sd["encoder.offsets"].dtype == torch.int32 and sd["sigma_net.weights"].shape == (64 * (32 + 64 + 16),) and sd["color_net.weights"].shape == (64 * (32 + 128 + 16),)
+    path = str(tmp_path / "ckpt.pth")
+    torch.save({"epoch": 3, "global_step": 100, "stats": {}, "model": sd}, path)
+    ck = torch.load(path, map_location="cpu")
+    missing, unexpected = b.load_state_dict(ck["model"], strict=True)
+    assert not missing and not unexpected
+    for k, v in b.state_dict().items():
+        assert torch.equal(v, sd[k]), k

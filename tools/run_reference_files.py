@@ -139,6 +139,8 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--out", default=None, help=".npz with image / depth")
     ap.add_argument("--time", type=int, default=0, help="timed frames (CUDA events, L2 flushed between frames)")
+    ap.add_argument("--save-ckpt", default=None, help="write a checkpoint in the layout of Trainer.save_checkpoint (nerf/utils.py:1485-1521)")
+    ap.add_argument("--load-ckpt", default=None, help="load such a checkpoint the way Trainer.load_checkpoint does (nerf/utils.py:1553-1574) instead of seeding the scene")
     args = ap.parse_args()
     if not available(args.backend):
         print(json.dumps({"unavailable": "reference files not staged (tools/stage_reference.py) or oracle/_ref missing"}))
@@ -149,7 +151,18 @@ def main():
     torch.cuda.set_device(0)
     NeRFNetwork, raymarching = import_reference_network(args.backend)
     from nerf_texture_b200 import scene
-    model = build_model(NeRFNetwork, dev)
+    if args.load_ckpt:
+        model = NeRFNetwork(encoding="hashgrid", bound=1, cuda_ray=True)
+        ckpt = torch.load(args.load_ckpt, map_location=dev)
+        missing, unexpected = model.load_state_dict(ckpt["model"], strict=False)       # utils.py:1560
+        assert not missing and not unexpected, (missing, unexpected)
+        model.mean_count, model.mean_density = ckpt["mean_count"], ckpt["mean_density"]
+        model = model.to(dev).eval()
+    else:
+        model = build_model(NeRFNetwork, dev)
+    if args.save_ckpt:
+        torch.save({"epoch": 1, "global_step": 1, "stats": {}, "mean_count": model.mean_count, "mean_density": model.mean_density, "model": model.state_dict()},
+                   args.save_ckpt)
     rays_o, rays_d = scene.pinhole_rays(args.size, args.size, dev)
     calls = {"march_rays": 0, "samples": 0}
     orig_march = raymarching.march_rays
