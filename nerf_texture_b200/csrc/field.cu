@@ -16,8 +16,9 @@
 //     back into tensor memory (tcgen05.st) as the A operand of the next layer's MMA (A-from-TMEM form).  Hidden activations,
 //     geo_feat and the SH basis never exist in shared memory: no STS, no generic->async proxy fence in the layer chain, and the
 //     16 KB activation buffer of round 1 is gone (the gather's throughput follows the L1 capacity the carve-out leaves);
-//   * the MMA -> epilogue chain is 7 dependent stages per tile; one tile per CTA is in flight (two resident CTAs per SM give
-//     the tensor pipe a second chain to interleave with) — ping-pong inside a CTA measured slower in round 1;
+//   * the MMA -> epilogue chain is 7 dependent stages per tile, one tile per CTA in flight (two resident CTAs per SM interleave
+//     their chains); the consumer loop is written for kCtx tiles in flight, but ping-pong between two TMEM contexts measured
+//     slower in both rounds (see kCtx);
 //   * shared memory is kept small on purpose: weights 36 KB + the producer->consumer feature ring.
 // Only xyz/dir (24 B) come in and sigma/rgb (16 B) go out per sample.
 #include "grid_common.cuh"
@@ -41,8 +42,17 @@ constexpr int kFW = 64;          // hidden width of both MLPs
 constexpr int kColorIn = 32;     // SH(16) + geo_feat(15) + zero pad (network_ff.py:42,95-97)
 constexpr int kFieldMaxLevels = 32;
 constexpr int kStages = NTX_FIELD_STAGES;       // feature tiles in the producer -> consumer ring
-constexpr uint32_t kOpndCol = 64;      // fp16 A operand [128 x 64] of the next layer: 32 columns behind the accumulator
-constexpr uint32_t kFieldTmemCols = 128;
+#ifndef NTX_FIELD_CTX
+#define NTX_FIELD_CTX 1
+#endif
+// Tiles a CTA's consumers keep in flight (TMEM contexts they alternate between).  2 measured SLOWER again in round 2, although with
+// the activations in tensor memory a second context no longer costs shared memory: frame 6.48 -> 8.05 ms, cfg2 coherent 201 -> 252 us,
+// MLP chain alone 124 -> 147 us (profiles/r02_summary.md) — the chain's time is the TMEM -> register read of the accumulators
+// (32 KB per hidden layer at ~64 B/clk per SM), which a second context shares instead of hiding.  The loop below stays generic.
+constexpr int kCtx = NTX_FIELD_CTX;
+constexpr uint32_t kOpndCol = 64;      // fp16 A operand [128 x 64] of the next layer: 32 columns behind the fp32 accumulator [128 x 64]
+constexpr uint32_t kCtxCols = 96;      // accumulator + operand columns of one context
+constexpr uint32_t kFieldTmemCols = kCtx == 1 ? 128 : 256;   // kCtx * kCtxCols rounded up to a power of two
 
 struct FieldPlan {
     uint32_t k0;                 // sigma-net input width = 2L
@@ -171,8 +181,8 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
     PairLevel* lv = reinterpret_cast<PairLevel*>(smem + plan.lv_off);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + plan.misc_off);        // [kStages] producers -> consumer
     uint64_t* empty_bar = full_bar + kStages;                                      // [kStages] consumer (MMA completion) -> producers
-    uint64_t* mma_bar = empty_bar + kStages;                                       // layer done -> consumer warps
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+    uint64_t* mma_bar = empty_bar + kStages;                                       // [kCtx] layer done -> consumer warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + kCtx);
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t K0 = plan.k0;
@@ -180,7 +190,7 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
     // ---- one-time setup (all 16 warps) ---------------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) { tc::mbar_init(&full_bar[s], kTasksPerTile); tc::mbar_init(&empty_bar[s], 1); }
-        tc::mbar_init(mma_bar, 1);
+        for (int c = 0; c < kCtx; c++) tc::mbar_init(&mma_bar[c], 1);
         tc::fence_mbar_init();
     }
     if (warp == 0) tc::tmem_alloc<kFieldTmemCols>(tmem_slot);
@@ -286,106 +296,122 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
         if (pw == 0 && lane == 0) PROBE_FLUSH(4)
     } else {
         // =============================== CONSUMERS: the two MLPs, activations resident in tensor memory =============
+        // kCtx tiles (contexts) in flight: each has its own accumulator + operand columns and its own MMA barrier; with kCtx = 2 the
+        // four warps alternate between them stage by stage (one tile's MMA under the other tile's epilogue).
         const uint32_t ws_addr = tc::smem_u32(ws_smem), wc_addr = tc::smem_u32(wc_smem);
         const uint32_t quarter = warp, row = quarter * 32 + lane;
-        const uint32_t acc_all = tmem_base, opnd_all = tmem_base + kOpndCol;                 // MMA addresses (all 128 lanes)
-        const uint32_t acc = acc_all + ((quarter * 32u) << 16), opnd = opnd_all + ((quarter * 32u) << 16);   // this warp's lanes
         const uint32_t nst = DENSITY ? ns + 1 : ns + nc + 2;      // density mode: the sigma net only
-        uint32_t ph = 0;
+        uint32_t ph[kCtx] = {};
         PROBE_DECL
-        for (uint32_t k = 0;; k++) {
-            const uint32_t tile = blockIdx.x + k * gridDim.x;
-            if (tile >= ntiles) break;
-            const uint32_t s = k % kStages, use = k / kStages;
-            uint32_t b = tile * kTileRows + row;
-            const bool ok = b < M;                        // this thread's row exists (ragged last tile)
-            float dx = 0.f, dy = 0.f, dz = 0.f;           // view direction of this row: its SH basis is evaluated between the two nets
-            if (DENSITY) { if (ok && dens.cells) b = (uint32_t)dens.cells[b]; }
-            else if (RAYS) {
-                if (ok) {
-                    const int2 e = rays.live[b];
-                    b = (uint32_t)e.x;                     // sigma / rgb go to the sample's slot row, where composite_rays looks for them
-                    const float* d = rays.rays_d + (size_t)e.y * 3;
-                    dx = d[0]; dy = d[1]; dz = d[2];
-                }
-            } else if (ok && rows) b = (uint32_t)rows[b];
-            const bool dead = MODE == MODE_ROWS && (!ok || (deltas && deltas[(size_t)b * 2] == 0.0f));
-            if (MODE == MODE_ROWS && ok) { dx = dirs[(size_t)b * 3]; dy = dirs[(size_t)b * 3 + 1]; dz = dirs[(size_t)b * 3 + 2]; }
-            PROBE_MARK(2)
-            // Only the issuing warp waits for the feature tile: nobody else reads it, and a consumer warp still polling
-            // full_bar[s] after the slot has been released below could see the producers complete the NEXT phase of that
-            // barrier and wait forever on a parity that has come round again.
-            if (warp == 0) { tc::mbar_wait(&full_bar[s], use & 1u); tc::tc_fence_after_sync(); }
-            PROBE_MARK(0)
-#ifdef NTX_DEV_PROBES
-            if (dbg & 2u) {   // producer-only timing: release the slot at once, skip both MLPs
-                if (tid == 0) tc::mbar_arrive(&empty_bar[s]);
-                if (ok) { st_stream_f32(sigmas + b, 0.f); for (int q = 0; q < 3; q++) st_stream_f32(rgbs + (size_t)b * 3 + q, 0.f); }
-                continue;
-            }
-#endif
-            if (warp == 0 && tc::elect_one()) {
-                issue_layer(tc::smem_u32(a0_smem + s * plan.a0_stage), ws_addr, K0, kFW, acc_all);
-                tc::mma_commit(mma_bar);
-                tc::mma_commit(&empty_bar[s]);   // the feature tile is free again as soon as this MMA has read it
-            }
-            for (uint32_t st = 0; st < nst; st++) {
-                tc::mbar_wait(mma_bar, ph); ph ^= 1;
-                PROBE_MARK(1)
-                tc::tc_fence_after_sync();
-                if (st == ns) {
-                    uint32_t v[16];
-                    tc::tmem_ld_x16(acc, v);
-                    tc::tmem_wait_ld();
-                    // h = fp16(W2 . a)   (FFMLP output is fp16); sigma = trunc_exp(h[0]) = exp(float(h[0]))   (network_ff.py:88)
-                    uint32_t hb[8];
+        for (uint32_t k0 = 0;; k0 += kCtx) {
+            if (blockIdx.x + k0 * gridDim.x >= ntiles) break;
+            uint32_t b[kCtx], aux[kCtx];                  // output row | ray index (MODE_RAYS)
+            bool has[kCtx], ok[kCtx], dead[kCtx];
+            float dxs[kCtx], dys[kCtx], dzs[kCtx];        // view direction of the row (its SH basis is evaluated between the two nets): loaded
+                                                          // when the tile starts — a load issued at the stage that needs it sits on the chain's
+                                                          // critical path (measured: frame 6.48 -> 7.36 ms)
 #pragma unroll
-                    for (int j = 0; j < 8; j++) hb[j] = float2_to_half2_bits(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                    const float h0 = __low2float(*reinterpret_cast<const __half2*>(&hb[0]));
-                    if (DENSITY) {
-                        // sigmas = trunc_exp(h[..., 0]); sigmas *= density_scale; tmp_grid[cas, indices] = sigmas   (network_ff.py:113, renderer.py:600-602)
-                        if (ok) dens.tmp[b] = __fmul_rn(expf(h0), density_scale);
-                    } else {
-                    if (ok) st_stream_f32(sigmas + b, dead ? 0.0f : density_scale * expf(h0));
-                    // colour-net input [128 x 32] = SH(dir) ++ h[1..15] ++ 0   (network_ff.py:93-97) -> 16 operand columns.
-                    // SH in fp32, rounded to fp16 when it enters the fp16 MLP.
-                    uint32_t o[16];
-                    {
-                        float sh[16];
-                        sh_basis<4, false>(dx, dy, dz, sh, nullptr, nullptr, nullptr);
-#pragma unroll
-                        for (int j = 0; j < 8; j++) o[j] = float2_to_half2_bits(sh[2 * j], sh[2 * j + 1]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 7; j++) o[8 + j] = __byte_perm(hb[j], hb[j + 1], 0x5432);
-                    o[15] = __byte_perm(hb[7], 0u, 0x5432);
-                    tc::tmem_st_x16(opnd, o);
-                    }
-                } else if (st + 1 == nst) {
-                    uint32_t v[8];
-                    tc::tmem_ld_x8(acc, v);
-                    tc::tmem_wait_ld();
-                    if (ok) {
-#pragma unroll
-                        for (int q = 0; q < 3; q++) {
-                            // rgb = sigmoid(h) evaluated on the fp16 output in fp32 and rounded back to fp16 (torch.sigmoid on a half tensor)
-                            const float hc = __half2float(__float2half_rn(__uint_as_float(v[q])));
-                            const float sg = 1.0f / (1.0f + expf(-hc));
-                            st_stream_f32(rgbs + (size_t)b * 3 + q, dead ? 0.0f : __half2float(__float2half_rn(sg)));
-                        }
-                    }
-                } else {
-                    field_hidden_epilogue(acc, opnd);
-                }
-                // epilogue done by all four warps: the next layer may read the operand columns and overwrite the accumulator
-                // (after the last stage: the next tile's first layer may)
-                tc::tmem_wait_st(); tc::tc_fence_before_sync(); consumer_sync();
-                if (st + 1 < nst && warp == 0 && tc::elect_one()) {
-                    tc::tc_fence_after_sync();
-                    field_issue_stage(st + 1, ns, nc, K0, opnd_all, ws_addr, wc_addr, acc_all);
-                    tc::mma_commit(mma_bar);
+            for (int c = 0; c < kCtx; c++) {
+                const uint32_t k = k0 + c, tile = blockIdx.x + k * gridDim.x;
+                has[c] = tile < ntiles;
+                b[c] = tile * kTileRows + row; aux[c] = 0; ok[c] = false; dead[c] = false;
+                if (!has[c]) continue;
+                const uint32_t s = k % kStages, use = k / kStages;
+                ok[c] = b[c] < M;                         // this thread's row exists (ragged last tile)
+                if (DENSITY) { if (ok[c] && dens.cells) b[c] = (uint32_t)dens.cells[b[c]]; }
+                else if (RAYS) {
+                    if (ok[c]) { const int2 e = rays.live[b[c]]; b[c] = (uint32_t)e.x; aux[c] = (uint32_t)e.y; }   // sigma / rgb go to the sample's slot row
+                } else if (ok[c] && rows) b[c] = (uint32_t)rows[b[c]];
+                dead[c] = MODE == MODE_ROWS && (!ok[c] || (deltas && deltas[(size_t)b[c] * 2] == 0.0f));
+                dxs[c] = dys[c] = dzs[c] = 0.f;
+                if (!DENSITY && ok[c]) {
+                    const float* d = RAYS ? rays.rays_d + (size_t)aux[c] * 3 : dirs + (size_t)b[c] * 3;
+                    dxs[c] = d[0]; dys[c] = d[1]; dzs[c] = d[2];
                 }
                 PROBE_MARK(2)
+                // Only the issuing warp waits for the feature tile: nobody else reads it, and a consumer warp still polling
+                // full_bar[s] after the slot has been released below could see the producers complete the NEXT phase of that
+                // barrier and wait forever on a parity that has come round again.
+                if (warp == 0) { tc::mbar_wait(&full_bar[s], use & 1u); tc::tc_fence_after_sync(); }
+                PROBE_MARK(0)
+#ifdef NTX_DEV_PROBES
+                if (dbg & 2u) {   // producer-only timing: release the slot at once, skip both MLPs
+                    if (tid == 0) tc::mbar_arrive(&empty_bar[s]);
+                    if (ok[c] && sigmas) { st_stream_f32(sigmas + b[c], 0.f); for (int q = 0; q < 3; q++) st_stream_f32(rgbs + (size_t)b[c] * 3 + q, 0.f); }
+                    has[c] = false;
+                    continue;
+                }
+#endif
+                if (warp == 0 && tc::elect_one()) {
+                    issue_layer(tc::smem_u32(a0_smem + s * plan.a0_stage), ws_addr, K0, kFW, tmem_base + c * kCtxCols);
+                    tc::mma_commit(&mma_bar[c]);
+                    tc::mma_commit(&empty_bar[s]);   // the feature tile is free again as soon as this MMA has read it
+                }
+            }
+            for (uint32_t st = 0; st < nst; st++) {
+#pragma unroll
+                for (int c = 0; c < kCtx; c++) {
+                    if (!has[c]) continue;
+                    const uint32_t acc_all = tmem_base + c * kCtxCols, opnd_all = acc_all + kOpndCol;        // MMA addresses (all 128 lanes)
+                    const uint32_t acc = acc_all + ((quarter * 32u) << 16), opnd = opnd_all + ((quarter * 32u) << 16);   // this warp's lanes
+                    const float dx = dxs[c], dy = dys[c], dz = dzs[c];
+                    tc::mbar_wait(&mma_bar[c], ph[c]); ph[c] ^= 1;
+                    PROBE_MARK(1)
+                    tc::tc_fence_after_sync();
+                    if (st == ns) {
+                        uint32_t v[16];
+                        tc::tmem_ld_x16(acc, v);
+                        tc::tmem_wait_ld();
+                        // h = fp16(W2 . a)   (FFMLP output is fp16); sigma = trunc_exp(h[0]) = exp(float(h[0]))   (network_ff.py:88)
+                        uint32_t hb[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) hb[j] = float2_to_half2_bits(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                        const float h0 = __low2float(*reinterpret_cast<const __half2*>(&hb[0]));
+                        if (DENSITY) {
+                            // sigmas = trunc_exp(h[..., 0]); sigmas *= density_scale; tmp_grid[cas, indices] = sigmas   (network_ff.py:113, renderer.py:600-602)
+                            if (ok[c]) dens.tmp[b[c]] = __fmul_rn(expf(h0), density_scale);
+                        } else {
+                            if (ok[c]) st_stream_f32(sigmas + b[c], dead[c] ? 0.0f : density_scale * expf(h0));
+                            // colour-net input [128 x 32] = SH(dir) ++ h[1..15] ++ 0   (network_ff.py:93-97) -> 16 operand columns.
+                            // SH in fp32, rounded to fp16 when it enters the fp16 MLP.
+                            uint32_t o[16];
+                            {
+                                float sh[16];
+                                sh_basis<4, false>(dx, dy, dz, sh, nullptr, nullptr, nullptr);
+#pragma unroll
+                                for (int j = 0; j < 8; j++) o[j] = float2_to_half2_bits(sh[2 * j], sh[2 * j + 1]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 7; j++) o[8 + j] = __byte_perm(hb[j], hb[j + 1], 0x5432);
+                            o[15] = __byte_perm(hb[7], 0u, 0x5432);
+                            tc::tmem_st_x16(opnd, o);
+                        }
+                    } else if (st + 1 == nst) {
+                        uint32_t v[8];
+                        tc::tmem_ld_x8(acc, v);
+                        tc::tmem_wait_ld();
+                        if (ok[c]) {
+#pragma unroll
+                            for (int q = 0; q < 3; q++) {
+                                // rgb = sigmoid(h) evaluated on the fp16 output in fp32 and rounded back to fp16 (torch.sigmoid on a half tensor)
+                                const float hc = __half2float(__float2half_rn(__uint_as_float(v[q])));
+                                const float sg = 1.0f / (1.0f + expf(-hc));
+                                st_stream_f32(rgbs + (size_t)b[c] * 3 + q, dead[c] ? 0.0f : __half2float(__float2half_rn(sg)));
+                            }
+                        }
+                    } else {
+                        field_hidden_epilogue(acc, opnd);
+                    }
+                    // epilogue done by all four warps: this tile's next layer may read the operand columns and overwrite the
+                    // accumulator (after the last stage: the next tile of this context may)
+                    tc::tmem_wait_st(); tc::tc_fence_before_sync(); consumer_sync();
+                    if (st + 1 < nst && warp == 0 && tc::elect_one()) {
+                        tc::tc_fence_after_sync();
+                        field_issue_stage(st + 1, ns, nc, K0, opnd_all, ws_addr, wc_addr, acc_all);
+                        tc::mma_commit(&mma_bar[c]);
+                    }
+                    PROBE_MARK(2)
+                }
             }
         }
         if (tid == 0) PROBE_FLUSH(0)

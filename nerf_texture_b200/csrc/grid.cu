@@ -181,17 +181,29 @@ __global__ void __launch_bounds__(kPairThreads, 3) grid_fwd_pair_kernel(
 
 // ---------------------------------------------------------------------------------------------------- backward
 template <typename T> struct AtomicAdd2;  // add two adjacent channels
+// add_pair: two adjacent 2-channel entries (an aligned 4-scalar slot) in one vector reduction (sm_90+ `red.v2.f16x2` / `red.v4.f32`)
 template <> struct AtomicAdd2<float> {
+    static constexpr bool kHasPairAdd = true;
     static __device__ __forceinline__ void add(float* p, float a, float b) { atomicAdd(reinterpret_cast<float2*>(p), make_float2(a, b)); }
     static __device__ __forceinline__ void add1(float* p, float a) { atomicAdd(p, a); }
+    static __device__ __forceinline__ void add_pair(float* p, float a0, float b0, float a1, float b1) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a0), "f"(b0), "f"(a1), "f"(b1) : "memory");
+    }
 };
 template <> struct AtomicAdd2<double> {
+    static constexpr bool kHasPairAdd = false;
     static __device__ __forceinline__ void add(double* p, double a, double b) { atomicAdd(p, a); atomicAdd(p + 1, b); }
     static __device__ __forceinline__ void add1(double* p, double a) { atomicAdd(p, a); }
+    static __device__ __forceinline__ void add_pair(double* p, double a0, double b0, double a1, double b1) { add(p, a0, b0); add(p + 2, a1, b1); }
 };
 template <> struct AtomicAdd2<__half> {
+    static constexpr bool kHasPairAdd = true;
     static __device__ __forceinline__ void add(__half* p, __half a, __half b) { atomicAdd(reinterpret_cast<__half2*>(p), __halves2half2(a, b)); }
     static __device__ __forceinline__ void add1(__half* p, __half a) { atomicAdd(p, a); }
+    static __device__ __forceinline__ void add_pair(__half* p, __half a0, __half b0, __half a1, __half b1) {
+        const __half2 lo = __halves2half2(a0, b0), hi = __halves2half2(a1, b1);
+        asm volatile("red.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(p), "r"(*reinterpret_cast<const uint32_t*>(&lo)), "r"(*reinterpret_cast<const uint32_t*>(&hi)) : "memory");
+    }
 };
 
 // one thread per (sample, level, channel pair); level is the fastest index inside a warp's sample so that a warp's
@@ -232,17 +244,36 @@ __global__ void __launch_bounds__(256) grid_bwd_kernel(
 #pragma unroll
         for (uint32_t c = 0; c < NC; c++) gc[c] = gp[c];
         scalar_t* gg = grad_grid + (size_t)g.offset * C + ch;
+        // corners are visited in x-pairs (idx, idx + 1): the two entries of a pair differ in the x coordinate only
 #pragma unroll
-        for (uint32_t idx = 0; idx < (1u << D); idx++) {
-            float w = 1; uint32_t pl[D];
+        for (uint32_t idx = 0; idx < (1u << D); idx += 2) {
+            float w0 = 1 - pos[0], w1 = pos[0]; uint32_t pl[D];
+            pl[0] = pg[0];
 #pragma unroll
-            for (uint32_t d = 0; d < D; d++) {
-                if ((idx & (1u << d)) == 0) { w *= 1 - pos[d]; pl[d] = pg[d]; }
-                else { w *= pos[d]; pl[d] = pg[d] + 1; }
+            for (uint32_t d = 1; d < D; d++) {
+                if ((idx & (1u << d)) == 0) { w0 *= 1 - pos[d]; w1 *= 1 - pos[d]; pl[d] = pg[d]; }
+                else { w0 *= pos[d]; w1 *= pos[d]; pl[d] = pg[d] + 1; }
             }
-            const uint32_t index = corner_index<D>(g, pl) * C;
-            if (NC == 2) AtomicAdd2<scalar_t>::add(gg + index, Num<scalar_t>::wmul(w, gc[0]), Num<scalar_t>::wmul(w, gc[NC - 1]));
-            else AtomicAdd2<scalar_t>::add1(gg + index, Num<scalar_t>::wmul(w, gc[0]));
+            const uint32_t i0 = corner_index<D>(g, pl);
+            pl[0] = pg[0] + 1;
+            const uint32_t i1 = corner_index<D>(g, pl);
+            if (NC == 2) {
+                const scalar_t a0 = Num<scalar_t>::wmul(w0, gc[0]), b0 = Num<scalar_t>::wmul(w0, gc[NC - 1]);
+                const scalar_t a1 = Num<scalar_t>::wmul(w1, gc[0]), b1 = Num<scalar_t>::wmul(w1, gc[NC - 1]);
+                // The two table entries of an x-pair share an aligned 2-entry slot whenever the cell's x is even (dense levels: they are
+                // neighbours; hashed levels: prime[0] == 1, so x and x + 1 differ in index bit 0 only): ONE vector reduction then does the
+                // work of two — the scatter is bound by the L2's reduction rate (~128 G red/s measured), not by bytes.
+                if (C == 2 && (i0 ^ i1) == 1u && AtomicAdd2<scalar_t>::kHasPairAdd) {
+                    if (i0 < i1) AtomicAdd2<scalar_t>::add_pair(gg + (size_t)i0 * C, a0, b0, a1, b1);
+                    else AtomicAdd2<scalar_t>::add_pair(gg + (size_t)i1 * C, a1, b1, a0, b0);
+                } else {
+                    AtomicAdd2<scalar_t>::add(gg + (size_t)i0 * C, a0, b0);
+                    AtomicAdd2<scalar_t>::add(gg + (size_t)i1 * C, a1, b1);
+                }
+            } else {
+                AtomicAdd2<scalar_t>::add1(gg + (size_t)i0 * C, Num<scalar_t>::wmul(w0, gc[0]));
+                AtomicAdd2<scalar_t>::add1(gg + (size_t)i1 * C, Num<scalar_t>::wmul(w1, gc[0]));
+            }
         }
     }
 }

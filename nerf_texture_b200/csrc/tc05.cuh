@@ -27,37 +27,37 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
 }
-// spin until the phase with the given parity has completed; traps instead of hanging forever if it never does
+// Wait until the phase with the given parity has completed.  try_wait suspends the thread in hardware for a bounded time and is
+// woken by the completing arrive; the loop re-arms it.  A suspend-time hint (NTX_MBAR_HINT_NS > 0: the compiler emits
+// TRYWAIT + NANOSLEEP.SYNCS) issues fewer instructions while waiting but wakes later: measured 1 % slower on the frame and 5 % on the
+// stand-alone MLP (profiles/r02_summary.md), so the default is the plain form.  Traps instead of hanging forever if the phase never
+// completes.
+#ifndef NTX_MBAR_HINT_NS          // development sweeps: -DNTX_MBAR_HINT_NS=10000 = suspend-time hint of 10 us
+#define NTX_MBAR_HINT_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
-    for (uint32_t spin = 0; !done; ++spin) {
-        asm volatile(
-            "{\n .reg .pred p;\n"
-            " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            " selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (spin > (1u << 24)) __trap();
-    }
-}
-
-// same for waits that are not latency-critical (a producer waiting for a free slot): sleep between polls instead of burning
-// issue slots — a spinning warp competes with the working warps of its scheduler (ncu: 21 % of all issued instructions
-// were this loop, and the consumer warps it was waiting for ran at half speed)
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t sleep_ns) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
     for (uint32_t spin = 0;; ++spin) {
+#if NTX_MBAR_HINT_NS > 0
+        asm volatile(
+            "{\n .reg .pred p;\n"
+            " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            " selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done) : "r"(addr), "r"(parity), "r"((uint32_t)NTX_MBAR_HINT_NS) : "memory");
+#else
         asm volatile(
             "{\n .reg .pred p;\n"
             " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
             " selp.u32 %0, 1, 0, p;\n}"
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+#endif
         if (done) break;
-        asm volatile("nanosleep.u32 %0;" ::"r"(sleep_ns));
         if (spin > (1u << 24)) __trap();
     }
 }
+// same wait for the producers' slot recycling (kept as a separate name: call sites document which waits are latency-critical)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t /*sleep_ns*/) { mbar_wait(bar, parity); }
 
 // ---- proxies / fences -----------------------------------------------------------------------------------
 // make this thread's generic-proxy shared-memory writes visible to the async proxy (tensor core / TMA reads)

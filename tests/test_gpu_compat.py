@@ -181,3 +181,79 @@ def test_tinycudann_shim_self_consistency():
     assert hg.n_output_dims == 8 and hg(d01).shape == (64, 8)
     y.float().sum().backward()
     assert net.params.grad is not None and torch.isfinite(net.params.grad).all()
+
+
+def test_tinycudann_shim_maps_bit_for_bit_onto_the_in_tree_ops():
+    """tiny-cuda-nn itself is absent (un-vendored, un-pinned: SURVEY F2), so the shim cannot be pinned against it; what CAN be pinned
+    is that it is nothing but the in-tree operators under tcnn's conventions: Network == FFMLP on the zero-padded input with the same
+    flat weights, SphericalHarmonics == SHEncoder(2x - 1), HashGrid == GridEncoder(2x - 1, bound=1), bit for bit."""
+    ntx()
+    import tinycudann as tcnn
+    from ffmlp import FFMLP
+    from gridencoder import GridEncoder
+    from shencoder import SHEncoder
+    g = torch.Generator().manual_seed(4)
+    x01 = torch.rand(3000, 3, generator=g).to(DEV)
+    # network: 3 matmuls for n_hidden_layers = 2  <->  FFMLP(num_layers = 2)
+    net = tcnn.Network(32, 16, {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None", "n_neurons": 64, "n_hidden_layers": 2}).to(DEV).eval()
+    mlp = FFMLP(32, 16, 64, 2).to(DEV).eval()
+    with torch.no_grad():
+        mlp.weights.copy_(net.params)
+    feat = (torch.rand(3000, 32, generator=g) - 0.5).to(DEV)
+    with torch.no_grad():
+        assert torch.equal(net(feat), mlp(feat))
+    # a ragged input width is zero-padded to a multiple of 16
+    net41 = tcnn.Network(41, 3, {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "Sigmoid", "n_neurons": 32, "n_hidden_layers": 1}).to(DEV).eval()
+    f41 = (torch.rand(500, 41, generator=g) - 0.5).to(DEV)
+    from nerf_texture_b200.operators import ffmlp_forward
+    with torch.no_grad():
+        want = ffmlp_forward(torch.nn.functional.pad(f41, (0, 7)), net41.params, 48, 16, 32, 1, 0, 3, True, False)[:, :3]
+        assert torch.equal(net41(f41), want)
+    # encodings
+    sh = tcnn.Encoding(3, {"otype": "SphericalHarmonics", "degree": 4}).to(DEV)
+    assert torch.equal(sh(x01), SHEncoder(3, 4).to(DEV)(x01 * 2 - 1).half())
+    cfg = {"otype": "HashGrid", "n_levels": 8, "n_features_per_level": 2, "log2_hashmap_size": 14, "base_resolution": 16, "per_level_scale": 1.5}
+    hg = tcnn.Encoding(3, cfg).to(DEV)
+    ge = GridEncoder(input_dim=3, num_levels=8, level_dim=2, per_level_scale=1.5, base_resolution=16, log2_hashmap_size=14, gridtype="hash", align_corners=False).to(DEV)
+    with torch.no_grad():
+        ge.embeddings.copy_(hg.enc.embeddings)
+        assert torch.equal(hg(x01), ge(x01 * 2 - 1, bound=1).half())
+
+
+def test_march_rays_train_differentiable_backward():
+    """raymarching.py:232-288: the backward pads grad_xyzs and the saved sample parameters t to [N * max_steps] rows, views them as
+    [N, max_steps, .] and returns grad_rays_o = sum_k g, grad_rays_d = sum_k g * t  (d xyz / d o = I, d xyz / d d = t, with t the parameter the marcher saved: the END of the sample's step).  The drop-in must
+    return exactly that function of ITS forward's samples; t of every sample is recovered here from the returned positions
+    (xyz = o + t d for the unclamped samples inside the ball) and the sums are formed in fp64."""
+    ntx()
+    import raymarching
+    from nerf_texture_b200 import scene
+    side, max_steps = 16, 64
+    N = side * side
+    rays_o, rays_d = scene.pinhole_rays(side, side, DEV)
+    bits = scene.ball_bitfield(1, 128, 1.0, DEV)
+    nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, torch.tensor([-1., -1, -1, 1, 1, 1], device=DEV), 0.2)
+    o = rays_o.clone().requires_grad_(True)
+    d = rays_d.clone().requires_grad_(True)
+    counter = torch.zeros(2, dtype=torch.int32, device=DEV)
+    xyzs, dirs, deltas, rays = raymarching.march_rays_train_differentiable(o, d, 1.0, bits, 1, 128, nears, fars, counter, -1, False, 128, True, 0.0, max_steps)
+    M = int(counter[0].item())
+    assert 0 < M <= xyzs.shape[0] <= N * max_steps
+    w = torch.randn(xyzs.shape, generator=torch.Generator().manual_seed(9)).to(DEV)
+    (w * xyzs).sum().backward()
+    # t of every real sample, from its owner ray (rays = [ray id, offset, count])
+    xn = xyzs.detach().cpu().numpy().astype(np.float64)
+    on, dn = rays_o.cpu().numpy().astype(np.float64), rays_d.cpu().numpy().astype(np.float64)
+    t = np.zeros(N * max_steps)
+    dl = deltas.detach().cpu().numpy().astype(np.float64)
+    for ray, off, cnt in rays.cpu().numpy():
+        if cnt > 0 and off + cnt <= M:
+            # the reference saves t AFTER the step (`t += dt; ...; rays_ts[0] = t`, raymarching.cu:655-658): position parameter + dt
+            t[off:off + cnt] = ((xn[off:off + cnt] - on[ray]) * dn[ray]).sum(1) / (dn[ray] ** 2).sum() + dl[off:off + cnt, 0]
+    g = np.zeros((N * max_steps, 3))
+    g[:xn.shape[0]] = w.cpu().numpy().astype(np.float64)
+    want_o = g.reshape(N, max_steps, 3).sum(1)
+    want_d = (g * t[:, None]).reshape(N, max_steps, 3).sum(1)
+    np.testing.assert_allclose(o.grad.cpu().numpy(), want_o, rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(d.grad.cpu().numpy(), want_d, rtol=2e-3, atol=2e-3 * max(1.0, np.abs(want_d).max()))
+    assert np.abs(want_d).max() > 1.0                                            # the check is not vacuous
