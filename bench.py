@@ -164,7 +164,7 @@ def reference_arm(args):
         phys = max(1, (os.cpu_count() or 2) // 2)
     os.environ["OMP_NUM_THREADS"] = str(phys)     # torchrun exports OMP_NUM_THREADS=1 for its workers: override it here
     os.environ.setdefault("OMP_PROC_BIND", "false")
-    value, dt, ns, cores, sample = cpu_render_sample(stride=6, steps=max(1, args.steps), warmup=min(1, args.warmup))
+    value, dt, ns, cores, sample = cpu_render_sample(stride=5, steps=max(1, args.steps), warmup=min(1, args.warmup))   # same sub-sample as cpu_baseline
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
@@ -287,7 +287,7 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": "render_1024x1024_network_ff_random_weights (BASELINE config 3%s)" % ("; rays sharded in interleaved 1024-ray tiles + one NCCL all_gather, config 4" if world > 1 else ""),
                    "field": "hashgrid L=16 T=2^19 F=2 fp16 -> FFMLP(32,16,64,2) -> SH4 -> FFMLP(32,3,64,3)", "rays": N, "samples_per_frame": samples_per_frame,
-                   "loop_iterations": iterations, "sample_schedule": "n_step = clamp(8N // n_alive, 1, 64) rounded to 4, walk budget %d, rays that cannot reach an occupied cell dropped before the first march (same image as the reference's clamp(N // n_alive, 1, 8): 43 iterations)" % render.WALK_BUDGET,
+                   "loop_iterations": iterations, "sample_schedule": "n_step = clamp(32N // n_alive, 1, 256) rounded to 4, walk budget %d, rays that cannot reach an occupied cell dropped before the first march (same image as the reference's clamp(N // n_alive, 1, 8): 43 iterations)" % render.WALK_BUDGET,
                    "max_steps": 1024, "dt_gamma": 0, "occupancy": "ball r=0.5, H=128, 1 cascade",
                    "l2": "flushed between timed steps (256 MiB memset)", "parallelism": "ray-sharded x%d" % world},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
@@ -326,11 +326,12 @@ def main():
         live = tk["n_samples"]
         nlaunch = tk["iterations"]
         achieved = live * FIELD_BYTES_PER_SAMPLE / kt / 1e9
-        traffic = None   # DRAM bytes of one in-frame launch from the committed `ncu --set full` capture (profiles/)
+        # DRAM bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of ALL field-kernel launches of one frame of this build
+        # (one ncu pass, tools/gpu/r2_final.sh -> profiles/r02_field_kernel_traffic.json), divided by the launches that did work
+        traffic = None
         try:
-            # the capture is of ONE (large) launch; scale its DRAM-bytes-per-algorithmic-byte to this run's average launch
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_field_kernel_traffic.json")))
-            traffic = int(tj["dram_bytes_per_algorithmic_byte"] * live * FIELD_BYTES_PER_SAMPLE / max(nlaunch, 1))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_field_kernel_traffic.json")))
+            traffic = int(tj["dram_bytes_all_field_launches_of_one_frame"] / max(nlaunch, 1))
         except Exception:
             pass
         line["roofline"] = {"bound": "hbm", "kernel": "ngp_field_kernel (hash-grid gather + sigma MLP + SH + colour MLP)", "achieved": achieved,

@@ -214,11 +214,9 @@ static int launch_dgrad(const __half* grad, const __half* w, const __half* fwd, 
 using namespace ntx;
 
 extern "C" size_t ntx_ffmlp_backward_workspace_bytes(uint32_t input_dim, uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers) {
-    // scratch of the weight-gradient kernels: kWgMaxParts partial sums of the largest [<=128 x <=256] gradient block (the layers run
-    // one after the other on the stream and reuse it)
-    (void)num_layers;
-    const size_t widest = std::min<size_t>(256, std::max<size_t>(std::max<size_t>(input_dim, hidden_dim), output_dim));
-    return sizeof(float) * (size_t)kWgMaxParts * std::min<size_t>(hidden_dim, 128) * widest;
+    // scratch of the weight-gradient kernel: kWgMaxParts partial sums of every parameter (all gradient blocks are computed in one launch)
+    const size_t params = (size_t)hidden_dim * ((size_t)input_dim + (size_t)hidden_dim * (num_layers - 1) + output_dim);
+    return sizeof(float) * (size_t)kWgMaxParts * params;
 }
 
 extern "C" int ntx_ffmlp_backward(const void* grad_, const void* inputs_, const void* weights_, const void* forward_buffer_, uint32_t B, uint32_t input_dim,
@@ -251,25 +249,36 @@ extern "C" int ntx_ffmlp_backward(const void* grad_, const void* inputs_, const 
         default: set_error("hidden_dim should in [16, 32, 64, 128, 256]"); return NTX_ERR_UNSUPPORTED;
     }
     if (rc != NTX_OK) return rc;
-    // weight gradients (layouts as ffmlp.cu:742-748).  dpre[j] = backward_buffer[n-1-j], n = num_layers.  One tcgen05 kernel + its
-    // reduce per [<=128 x <=256] gradient block; the scratch is reused block after block (stream order).
+    // weight gradients (layouts as ffmlp.cu:742-748).  dpre[j] = backward_buffer[n-1-j], n = num_layers.  Every [<=128 x <=256]
+    // gradient block is a job; all jobs run in ONE tcgen05 launch + ONE reduce.
     const uint32_t n = num_layers, Hd = hidden_dim;
     __half* gw0 = gw;                                            // [hidden, in]
     __half* gwh = gw + (size_t)Hd * input_dim;                   // (n-1) x [hidden, hidden]
     __half* gwl = gwh + (size_t)(n - 1) * Hd * Hd;               // [16, hidden]
+    WgJobs jobs;
+    uint32_t nj = 0;
+    auto add_job = [&](const __half* P, uint32_t ldp, uint32_t p, const __half* Q, uint32_t ldq, uint32_t q, bool transpose, __half* dst, uint32_t ld_dst) {
+        if (nj == kWgMaxJobs) return false;
+        WgJob& j = jobs.j[nj++];
+        j.P = P; j.Q = Q; j.partials = nullptr; j.dst = dst; j.ldp = ldp; j.p = p; j.ldq = ldq; j.q = q; j.ld_dst = ld_dst; j.transpose = transpose ? 1u : 0u;
+        j.tmem_cols = 0; j.pad = 0;
+        return true;
+    };
+    bool fits = true;
     for (uint32_t r0 = 0; r0 < Hd; r0 += 128) {
         const uint32_t pr = std::min<uint32_t>(128u, Hd - r0);
         // output layer: dW_last[16 x hidden] = grad^T . act[n-1], computed as (act[n-1][:, r0:r0+pr])^T . grad and stored transposed
-        if ((rc = launch_wgrad(fwd + (size_t)(n - 1) * B * Hd + r0, Hd, pr, grad, 16, 16, true, gwl + r0, Hd, ws, B, st)) != NTX_OK) return rc;
+        fits = fits && add_job(fwd + (size_t)(n - 1) * B * Hd + r0, Hd, pr, grad, 16, 16, true, gwl + r0, Hd);
         // hidden layers: dW_h[j][hidden x hidden] = dpre[j+1]^T . act[j]
         for (uint32_t j = 0; j + 1 < n; j++)
             for (uint32_t c0 = 0; c0 < Hd; c0 += 256)
-                if ((rc = launch_wgrad(bwd + (size_t)(n - 2 - j) * B * Hd + r0, Hd, pr, fwd + (size_t)j * B * Hd + c0, Hd, std::min<uint32_t>(256u, Hd - c0), false,
-                                       gwh + (size_t)j * Hd * Hd + (size_t)r0 * Hd + c0, Hd, ws, B, st)) != NTX_OK) return rc;
+                fits = fits && add_job(bwd + (size_t)(n - 2 - j) * B * Hd + r0, Hd, pr, fwd + (size_t)j * B * Hd + c0, Hd, std::min<uint32_t>(256u, Hd - c0), false,
+                                       gwh + (size_t)j * Hd * Hd + (size_t)r0 * Hd + c0, Hd);
         // first layer: dW_0[hidden x in] = dpre[0]^T . inputs
         for (uint32_t c0 = 0; c0 < input_dim; c0 += 256)
-            if ((rc = launch_wgrad(bwd + (size_t)(n - 1) * B * Hd + r0, Hd, pr, inputs + c0, input_dim, std::min<uint32_t>(256u, input_dim - c0), false,
-                                   gw0 + (size_t)r0 * input_dim + c0, input_dim, ws, B, st)) != NTX_OK) return rc;
+            fits = fits && add_job(bwd + (size_t)(n - 1) * B * Hd + r0, Hd, pr, inputs + c0, input_dim, std::min<uint32_t>(256u, input_dim - c0), false,
+                                   gw0 + (size_t)r0 * input_dim + c0, input_dim);
     }
-    return NTX_OK;
+    NTX_REQUIRE(fits, NTX_ERR_UNSUPPORTED, "ffmlp_backward: more than %d weight-gradient blocks (hidden_dim %u, input_dim %u, num_layers %u)", kWgMaxJobs, Hd, input_dim, n);
+    return launch_wgrad_jobs(jobs, nj, ws, B, st);
 }

@@ -19,7 +19,7 @@ namespace ntx {
 constexpr int kWgThreads = 256;
 constexpr uint32_t kWgSlab = 128;                               // batch rows per stage = K of 8 UMMAs
 constexpr uint32_t kWgSbo = kWgSlab * 16u + 16u;                // bytes between 8-row groups (+16: transposed stores hit 32 distinct banks)
-constexpr uint32_t kWgMaxParts = 320;                           // partial-sum slices in the workspace (two CTAs per SM of a B200)
+constexpr uint32_t kWgMaxParts = 480;                           // partial-sum slices per job in the workspace (three CTAs per SM of a B200)
 constexpr int kWgStages = 2;
 
 struct WgPlan { uint32_t a_bytes, b_bytes, stage_bytes, misc_off, total; };
@@ -53,9 +53,22 @@ __device__ __forceinline__ void stage_slab_transposed(uint8_t* dst, const __half
     }
 }
 
-__global__ void __launch_bounds__(kWgThreads) mlp_wgrad_tc_kernel(const __half* __restrict__ P, const uint32_t ldp, const uint32_t p,
-                                                                  const __half* __restrict__ Q, const uint32_t ldq, const uint32_t q,
-                                                                  float* __restrict__ partials, const uint32_t B, const uint32_t tmem_cols) {
+// one gradient block G = P^T Q of the backward pass; all blocks of a backward run in ONE launch (blockIdx.y = job) and one reduce
+struct WgJob {
+    const __half* P; const __half* Q;   // [B x ldp], [B x ldq] row-major; the first p / q columns are used
+    float* partials;                    // [gridDim.x][p * q] scratch
+    __half* dst;                        // fp16 result, leading dimension ld_dst; transposed: dst is [q x p]
+    uint32_t ldp, p, ldq, q, ld_dst, transpose, tmem_cols, pad;
+};
+constexpr int kWgMaxJobs = 12;
+struct WgJobs { WgJob j[kWgMaxJobs]; };
+
+__global__ void __launch_bounds__(kWgThreads) mlp_wgrad_tc_kernel(const __grid_constant__ WgJobs jobs, const uint32_t B) {
+    const WgJob& job = jobs.j[blockIdx.y];
+    const __half* __restrict__ P = job.P;
+    const __half* __restrict__ Q = job.Q;
+    float* __restrict__ partials = job.partials;
+    const uint32_t ldp = job.ldp, p = job.p, ldq = job.ldq, q = job.q, tmem_cols = job.tmem_cols;
     extern __shared__ __align__(1024) uint8_t smem[];
     const WgPlan plan = wg_plan(p, q);
     uint64_t* empty_bar = reinterpret_cast<uint64_t*>(smem + plan.misc_off);    // [kWgStages] the MMAs of a stage have read it
@@ -123,15 +136,18 @@ __global__ void __launch_bounds__(kWgThreads) mlp_wgrad_tc_kernel(const __half* 
     }
 }
 
-// dst (fp16) = sum over the CTAs' partial G[p x q] slices; transpose: dst is [q x p] with leading dimension ld_dst (the output
+// job.dst (fp16) = sum over the CTAs' partial G[p x q] slices of that job; transpose: dst is [q x p] with leading dimension ld_dst (the output
 // layer's gradient is produced as activations^T . dY and stored as dW[16 x hidden]).  A block owns 32 consecutive entries: warp w
 // sums slices w, w+8, ... (coalesced 128-byte reads, independent loads in flight), the eight per-warp sums are added in warp order —
 // a fixed summation tree, so the result does not depend on scheduling.
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partials, const uint32_t n_parts, const uint32_t p, const uint32_t q,
-                                                           const bool transpose, const uint32_t ld_dst, __half* __restrict__ dst) {
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ WgJobs jobs, const uint32_t n_parts) {
+    const WgJob& job = jobs.j[blockIdx.y];
+    const float* __restrict__ partials = job.partials;
+    const uint32_t p = job.p, q = job.q;
     __shared__ float s_part[8][33];
     const uint32_t n = p * q, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t i = blockIdx.x * 32u + lane;
+    if (blockIdx.x * 32u >= n) return;
     float acc = 0.f;
     if (i < n) {
 #pragma unroll 4
@@ -144,29 +160,41 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 #pragma unroll
         for (int w = 1; w < 8; w++) t += s_part[w][lane];
         const uint32_t r = i / q, col = i - r * q;
-        dst[transpose ? (size_t)col * ld_dst + r : (size_t)r * ld_dst + col] = __float2half_rn(t);
+        job.dst[job.transpose ? (size_t)col * job.ld_dst + r : (size_t)r * job.ld_dst + col] = __float2half_rn(t);
     }
 }
 
-// G = P^T Q -> dst (fp16, leading dimension ld_dst); `ws` = kWgMaxParts * p * q floats of scratch (no initialisation needed)
-static int launch_wgrad(const __half* P, uint32_t ldp, uint32_t p, const __half* Q, uint32_t ldq, uint32_t q, bool transpose, __half* dst, uint32_t ld_dst,
-                        float* ws, uint32_t B, cudaStream_t st) {
-    const WgPlan plan = wg_plan(p, q);
+// number of batch-slab CTAs per job (= partial-sum slices per job in the workspace)
+static uint32_t wgrad_parts(uint32_t B) {
+    const uint32_t nslabs = ceil_div<uint32_t>(B, kWgSlab);
+    return std::min<uint32_t>(nslabs, std::min<uint32_t>(3u * (uint32_t)device_sm_count(), kWgMaxParts));
+}
+
+// all jobs of one backward: ONE tcgen05 launch (grid = parts x jobs) + ONE reduce launch
+static int launch_wgrad_jobs(WgJobs& jobs, uint32_t njobs, float* ws, uint32_t B, cudaStream_t st) {
+    const uint32_t parts = wgrad_parts(B);
+    uint32_t smem = 0, max_n = 0;
+    size_t off = 0;
+    for (uint32_t i = 0; i < njobs; i++) {
+        WgJob& j = jobs.j[i];
+        smem = std::max(smem, wg_plan(j.p, j.q).total);
+        max_n = std::max(max_n, j.p * j.q);
+        j.tmem_cols = j.q <= 32 ? 32u : j.q <= 64 ? 64u : j.q <= 128 ? 128u : 256u;
+        j.partials = ws + off;
+        off += (size_t)parts * j.p * j.q;
+    }
     static uint32_t configured_dev[kMaxDevices] = {};
     uint32_t& configured = configured_dev[current_device()];
-    if (plan.total > configured) {
-        if (cudaFuncSetAttribute(mlp_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess) {
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(mlp_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             cudaGetLastError();
-            set_error("FullyFusedMLP backward: cannot reserve %u bytes of shared memory for the weight-gradient kernel", plan.total);
+            set_error("FullyFusedMLP backward: cannot reserve %u bytes of shared memory for the weight-gradient kernel", smem);
             return NTX_ERR_CUDA;
         }
-        configured = plan.total;
+        configured = smem;
     }
-    const uint32_t nslabs = ceil_div<uint32_t>(B, kWgSlab);
-    const uint32_t parts = std::min<uint32_t>(nslabs, std::min<uint32_t>(2u * (uint32_t)device_sm_count(), kWgMaxParts));
-    const uint32_t tmem_cols = q <= 32 ? 32u : q <= 64 ? 64u : q <= 128 ? 128u : 256u;
-    mlp_wgrad_tc_kernel<<<parts, kWgThreads, plan.total, st>>>(P, ldp, p, Q, ldq, q, ws, B, tmem_cols);
-    wgrad_reduce_kernel<<<ceil_div<uint32_t>(p * q, 32), 256, 0, st>>>(ws, parts, p, q, transpose, ld_dst, dst);
+    mlp_wgrad_tc_kernel<<<dim3(parts, njobs), kWgThreads, smem, st>>>(jobs, B);
+    wgrad_reduce_kernel<<<dim3(ceil_div<uint32_t>(max_n, 32), njobs), 256, 0, st>>>(jobs, parts);
     return check_launch("ffmlp_backward(wgrad)");
 }
 

@@ -126,7 +126,9 @@ __device__ __forceinline__ bool probe(const Ray& r, const MarchParams& p, float&
         const float ty = (((ny + 0.5f + 0.5f * signf1(r.dy)) * p.rH * 2 - 1) * p.mb0 - y) * r.rdy;
         const float tz = (((nz + 0.5f + 0.5f * signf1(r.dz)) * p.rH * 2 - 1) * p.mb0 - z) * r.rdz;
         const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
-        do { t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max); } while (t < tt);
+        // dt_gamma == 0: clamp(t * 0, dt_min, dt_max) is dt_min for every finite t — same additions, two instructions less per lattice step
+        if (p.dt_gamma == 0.0f) { do { t += p.dt_min; } while (t < tt); }
+        else { do { t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max); } while (t < tt); }
         return false;
     }
     const int level = max(mip_from_pos(x, y, z, p.C), mip_from_dt(dt, p.H, p.C));
@@ -911,7 +913,7 @@ __global__ void __launch_bounds__(kMarchThreads, 6) march_rays_staged_kernel(
 // per sample a thread keeps a whole speculation window of 8 samples in registers and writes it with six 16-byte stores (a ray's
 // rows are contiguous and 16-byte aligned when n_step % 4 == 0), so the shared-memory staging, its bank conflicts, the block
 // barriers around the copy-out (44 % of the staged kernel's stall samples) and the copy-out itself are gone.
-// live[i] = (row, ray index) of every filled row, appended per block (one block scan + one atomic per launch and block).
+// live[i] = (row, ray index) of every filled row, appended per warp (warp scan + one atomic per warp: no barrier in this kernel).
 __global__ void __launch_bounds__(kMarchThreads, 6) march_rays_compact_kernel(
     const int* __restrict__ rays_alive, const float* __restrict__ rays_t, const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float bound,
     const float dt_gamma, const uint32_t max_steps, const uint32_t C, const uint32_t H, const uint8_t* __restrict__ grid, const float* __restrict__ fars,
@@ -1019,13 +1021,19 @@ __global__ void __launch_bounds__(kMarchThreads, 6) march_rays_compact_kernel(
     if (mine && step < n_step) { pl[2 * step] = 0.f; pl[2 * step + 1] = paused ? -t : 0.f; }   // composite_rays stops at (0, .); (0, -t) = paused at t
     const uint32_t filled = mine ? step : 0u;
     {
-        __shared__ uint32_t s_scan[33];
-        __shared__ uint32_t s_base;
-        uint32_t total;
-        const uint32_t excl = block_exclusive_scan(filled, total, s_scan);
-        if (threadIdx.x == 0) s_base = total ? (uint32_t)atomicAdd(live_counter, (int)total) : 0u;
-        __syncthreads();
-        int2* __restrict__ dst = live + s_base + excl;
+        // Append this warp's rows to the live list: warp scan + ONE atomic per warp, no block barrier — a warp that has finished its
+        // rays retires instead of waiting for the slowest ray of its block (a third of the staged design's and of the first compact
+        // version's stall samples sat on that barrier).  Rows of a warp stay together and in ray order; warps append in arrival order.
+        __syncwarp();
+        const uint32_t lane = threadIdx.x & 31u;
+        uint32_t inc = filled;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        uint32_t base = 0;
+        if (lane == 31 && total) base = (uint32_t)atomicAdd(live_counter, (int)total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int2* __restrict__ dst = live + base + (inc - filled);
         for (uint32_t j = 0; j < filled; j++) dst[j] = make_int2((int)(row0 + j), index);
     }
     if (sample_counter && mine) {                                // bench / statistics only: samples emitted in this launch

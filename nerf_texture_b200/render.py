@@ -89,10 +89,12 @@ WALK_BUDGET = 16   # empty voxels a ray may cross per march before it pauses (nt
 
 
 def auto_schedule(N):
-    """(8N, 64): up to 64 samples per ray and iteration, 8N sample rows of workspace (436 MB for a 1024^2 frame).  Measured best
-    from 1/8 of a frame to a full frame (6-7 loop iterations instead of 43; since the field kernel runs over the marcher's
-    live-row list, rows past a ray's end cost nothing but their zero fill)."""
-    return (8, 64)
+    """(32N, 256): up to 256 samples per ray and iteration, 32N sample rows of workspace (36 B each: 1.2 GB for a 1024^2 frame).
+    Round-2 sweep (tools/schedule_sweep.py, profiles/r02_schedule_sweep.txt): 3 loop iterations instead of 7 with (8N, 64) and 43 with the
+    reference's (N, 8); full frame 6.35 -> 6.23 ms, a 1/8 shard 1.36 -> 1.21 ms (every iteration costs a march launch whose length is
+    a latency chain per ray, whatever the ray count).  The field kernel runs over the marcher's live-row list, so rows past a ray's
+    end cost nothing."""
+    return (32, 256)
 
 
 def _frame_buffers(dev, N, max_steps, budget, mailbox_len):
