@@ -219,7 +219,7 @@ def main():
     def step_device():
         # this rank's (resident) shard of the frame, rendered straight into its planar send block, + the tile all-gather and the
         # assembly kernel (config 4); one GPU: the frame
-        out = render.render_rays(field, my_o, my_d, bits, 1, 128, block_rows=n_max)
+        out = render.render_rays(field, my_o, my_d, bits, 1, 128, block_rows=n_max, cache_mip=True)
         return render.gather_frame(out, N) if world > 1 else out
 
     def barrier():
@@ -270,7 +270,7 @@ def main():
 
     def step_e2e():
         d_o.copy_(h_o, non_blocking=True); d_d.copy_(h_d, non_blocking=True)
-        out = render.render_rays(field, d_o, d_d, bits, 1, 128, block_rows=n_max)       # each rank uploads and renders its own shard
+        out = render.render_rays(field, d_o, d_d, bits, 1, 128, block_rows=n_max, cache_mip=True)       # each rank uploads and renders its own shard
         if world > 1:
             out = render.gather_frame(out, N)
         if rank == 0:

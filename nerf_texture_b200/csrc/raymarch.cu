@@ -1478,7 +1478,7 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
     // concurrent calls from several threads on one device take turns here; calls on different devices do not interact.
     static std::mutex frame_mutex[kMaxDevices];
     std::lock_guard<std::mutex> frame_lock(frame_mutex[current_device()]);
-    constexpr int kEvents = 4;
+    constexpr int kEvents = 8;
     static cudaEvent_t ev_dev[kMaxDevices][kEvents];
     static bool ev_ready_dev[kMaxDevices] = {};
     cudaEvent_t* ev = ev_dev[current_device()];
@@ -1488,11 +1488,16 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
             if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); set_error("render_rays: cannot create events"); return NTX_ERR_CUDA; }
         ev_ready = true;
     }
-    cudaMemsetAsync(w.state, 0, 2 * sizeof(FrameState), st);
-    cudaMemsetAsync(w.scan, 0, scan_ws_bytes(ceil_div<uint32_t>(N, kCompactThreads * kCompactItems)), st);
-    cudaMemsetAsync(weights_sum, 0, sizeof(float) * N, st);
-    cudaMemsetAsync(depth, 0, sizeof(float) * N, st);
-    cudaMemsetAsync(image, 0, sizeof(float) * 3 * N, st);
+    // state and scan workspace are adjacent (carve_frame_workspace): one memset; the three result arrays are one when they form the planar
+    // block [weights_sum | depth | rgb] of render.py / ntx_unshard_frame
+    cudaMemsetAsync(w.state, 0, (size_t)(reinterpret_cast<char*>(w.scan) - reinterpret_cast<char*>(w.state)) + scan_ws_bytes(ceil_div<uint32_t>(N, kCompactThreads * kCompactItems)), st);
+    if (depth == weights_sum + N && image == depth + N) {
+        cudaMemsetAsync(weights_sum, 0, sizeof(float) * 5 * N, st);
+    } else {
+        cudaMemsetAsync(weights_sum, 0, sizeof(float) * N, st);
+        cudaMemsetAsync(depth, 0, sizeof(float) * N, st);
+        cudaMemsetAsync(image, 0, sizeof(float) * 3 * N, st);
+    }
     near_far_kernel<<<ceil_div<uint32_t>(N, 128), 128, 0, st>>>(rays_o, rays_d, aabb, N, min_near, w.nears, w.fars);
     // Loop bounds.  Without pauses every iteration gives each living ray n_step samples, and `step` (their sum) reaching max_steps
     // ends the loop like the reference's `while step < max_steps`.  A paused ray spends iterations without sampling — at most
@@ -1504,6 +1509,11 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
     const uint32_t step_limit = max_steps + pause_iters * max_n_step, iter_limit = max_steps + pause_iters;
     // rays that cannot hit anything occupied start dead (see frame_init_kernel); not for the reference's exact iteration structure
     const bool prekill = walk_budget != 0 && occupancy_mip != nullptr;
+    // How many iterations the launching thread runs ahead of the one whose n_alive it has read.  1: grids shrink as soon as possible and
+    // at most two empty iterations are queued at the end.  Queueing 3 ahead was measured on an 8-GPU box to check whether the host's
+    // wake-up after each event limits a 1/8 shard: 1.45 -> 1.85 ms per frame — it does not; the extra empty launches and full-size
+    // grids cost more (NTX_FRAME_AHEAD overrides for experiments).
+    const uint32_t ahead = tunables().frame_ahead > 0 ? (uint32_t)std::min(tunables().frame_ahead, kEvents - 1) : 1u;
     uint32_t bound_rays = N, iterations = 0, kernels = 1;   // near_far
     // optional per-kernel timing (bench.py's roofline): CUDA events around every march and field launch of this frame
     constexpr uint32_t kProfIters = 256;
@@ -1552,13 +1562,14 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
                                                                                   depth, image, s_cur);
         kernels += 3;                                       // march, field, composite
         cudaEventRecord(ev[i % kEvents], st);
-        if (i >= 1) {
-            // iteration i-1 has certainly been planned once its event fires; iteration i is queued behind it, so the device
-            // never idles while this thread looks at the mailbox
-            if (cudaEventSynchronize(ev[(i - 1) % kEvents]) != cudaSuccess) return check_launch("render_rays");
-            const int alive = host_mailbox[i - 1];
-            if (alive <= 0) break;            // iteration i-1 found nothing alive; iteration i (already queued) is a no-op
-            iterations = i;                   // iterations 0 .. i-1 did work
+        if (i >= ahead) {
+            // iteration i-ahead has certainly been planned once its event fires; the iterations queued behind it keep the device busy
+            // while this thread looks at the mailbox
+            const uint32_t j = i - ahead;
+            if (cudaEventSynchronize(ev[j % kEvents]) != cudaSuccess) return check_launch("render_rays");
+            const int alive = host_mailbox[j];
+            if (alive <= 0) break;            // iteration j found nothing alive; the iterations queued after it are no-ops
+            iterations = j + 1;               // iterations 0 .. j did work
             bound_rays = (uint32_t)alive;     // n_alive never grows
         }
     }

@@ -124,7 +124,7 @@ def _aabb_tensor(bound, dev, cache={}):
 
 
 def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aabb=None, min_near=0.2, dt_gamma=0.0, max_steps=1024, bg_color=1.0,
-                perturb=0, count_samples=False, profile=None, use_mip=True, device_loop=True, mip=None, schedule="auto", time_kernels=False, block_rows=None):
+                perturb=0, count_samples=False, profile=None, use_mip=True, device_loop=True, mip=None, schedule="auto", time_kernels=False, block_rows=None, cache_mip=False):
     """Inference branch of NeRFRenderer.run_cuda (renderer.py:436-489).  rays_o/d [N,3] fp32 CUDA.
     Returns dict(image [N,3], depth [N], weights_sum [N], iterations, n_samples (if count_samples)).
     device_loop=True (default): the whole loop is ONE libntx call whose iteration state stays on the device (ntx_render_rays);
@@ -132,7 +132,8 @@ def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aab
     (bit-identical results; kept for profiling and as the parity reference of the device-driven loop).
     profile: optional list (stepwise loop only); gets one (start_event, stop_event, live_sample_count_tensor) per field-kernel launch.
     time_kernels (device loop only): also return march_ms / field_ms, the summed CUDA-event times of the frame's march and field launches.
-    mip: optional pre-built occupancy mip (ntx_build_occupancy_mip) of density_bitfield.
+    mip: optional pre-built occupancy mip (ntx_build_occupancy_mip) of density_bitfield; cache_mip=True keeps the mip this call
+    builds for as long as the bit-field tensor is unchanged (3 tiny kernels per frame otherwise: bench.py rebuilds it every frame).
     schedule (device loop only): "auto" (auto_schedule(N); the reference's when perturb != 0), "reference", "wide", or a
     (budget_multiple, max_n_step) pair — the image is the same either way, see include/ntx.h.
     block_rows (device loop only, used by the sharded path): return the raw planar result block [weights_sum | depth | rgb] padded to
@@ -146,8 +147,14 @@ def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aab
         aabb = _aabb_tensor(bound, dev)
     st = L.stream()
     if use_mip and mip is None and grid_size >= 16 and (grid_size & (grid_size - 1)) == 0:
-        mip = torch.empty(L.lib().ntx_occupancy_mip_bytes(int(cascade), int(grid_size)), dtype=torch.uint8, device=dev)
-        L.call("ntx_build_occupancy_mip", L.ptr(density_bitfield), int(cascade), int(grid_size), L.ptr(mip), st)
+        if cache_mip:
+            # built once per bit-field tensor and version counter (weak reference: see compat/raymarching), like the drop-in march_rays
+            from .compat.raymarching.raymarching import _occupancy_mip
+            hit = _occupancy_mip(density_bitfield, int(cascade), int(grid_size))
+            mip = None if hit is None else hit[1]
+        else:
+            mip = torch.empty(L.lib().ntx_occupancy_mip_bytes(int(cascade), int(grid_size)), dtype=torch.uint8, device=dev)
+            L.call("ntx_build_occupancy_mip", L.ptr(density_bitfield), int(cascade), int(grid_size), L.ptr(mip), st)
     if not use_mip:
         mip = None
     if device_loop and profile is None and N > 0:
