@@ -288,7 +288,7 @@ def main():
         "config": {"workload": "render_1024x1024_network_ff_random_weights (BASELINE config 3%s)" % ("; rays sharded in interleaved 1024-ray tiles + one NCCL all_gather, config 4" if world > 1 else ""),
                    "field": "hashgrid L=16 T=2^19 F=2 fp16 -> FFMLP(32,16,64,2) -> SH4 -> FFMLP(32,3,64,3)", "rays": N, "samples_per_frame": samples_per_frame,
                    "loop_iterations": iterations, "sample_schedule": "n_step = clamp(32N // n_alive, 1, 256) rounded to 4, walk budget %d, rays that cannot reach an occupied cell dropped before the first march (same image as the reference's clamp(N // n_alive, 1, 8): 43 iterations)" % render.WALK_BUDGET,
-                   "max_steps": 1024, "dt_gamma": 0, "occupancy": "ball r=0.5, H=128, 1 cascade",
+                   "max_steps": 1024, "dt_gamma": 0, "occupancy": "ball r=0.5, H=128, 1 cascade (its occupancy mip is built once and cached per bit-field version, like the drop-in march_rays)",
                    "l2": "flushed between timed steps (256 MiB memset)", "parallelism": "ray-sharded x%d" % world},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
@@ -341,6 +341,9 @@ def main():
                             "live_samples": live, "kernel_share_of_step": kt * 1e3 / ms, "march_kernel_ms": tk["march_ms"],
                             "msamples_per_s_in_kernel": live / kt / 1e6,
                             "tensor_note": "36864 FLOP/sample on tcgen05: %.1f TFLOP/s achieved inside the kernel" % (live * 36864 / kt / 1e12)}
+        # ---- BASELINE config 1: grid_encode forward L=4 T=2^14 F=2 on 4096 random points — the reference has no CPU path, so
+        #      the "CPU" number is the oracle port on the host cores; the GPU kernel on the same input next to it
+        line["cfg1"] = bench_cfg1(torch, L, device)
         # ---- BASELINE config 2: 2^20 samples through the fused field kernel and the stand-alone encoder ------------
         line["cfg2"] = bench_cfg2(torch, L, field, device, peaks)
         # ---- the reference's own CUDA kernels (rebuilt for sm_100a, oracle/_ref) on the same frame, when the build is present:
@@ -383,6 +386,36 @@ def run_tool(tool, arg_sets, names, key):
     if key in a and key in b and a[key] > 0:
         out["speedup_vs_reference_cuda"] = b[key] / a[key]
     return out
+
+
+def bench_cfg1(torch, L, device):
+    import numpy as np
+    from oracle import oracle as O
+    offs, pls = O.grid_offsets(3, 4, 2, per_level_scale=2, base_resolution=16, log2_hashmap_size=14, align_corners=False)
+    rng = np.random.default_rng(1)
+    emb = (rng.random((int(offs[-1]), 2), dtype=np.float32) * 2 - 1).astype(np.float32)
+    x = np.random.default_rng(0).random((4096, 3), dtype=np.float32)
+    ts = []
+    for it in range(55):
+        t0 = time.perf_counter()
+        O.grid_encode(x, emb, offs, pls, 16, gridtype=0, align_corners=False)
+        if it >= 5:
+            ts.append(time.perf_counter() - t0)
+    cpu_us = statistics.median(ts) * 1e6
+    xt, et, ot = torch.from_numpy(x).to(device), torch.from_numpy(emb).to(device), torch.from_numpy(np.asarray(offs, np.int32)).to(device)
+    out = torch.empty(4096, 8, device=device)
+    fn = lambda: L.call("ntx_grid_encode_forward", L.ptr(xt), L.ptr(et), L.ptr(ot), L.ptr(out), 4096, 3, 2, 4, 1.0, 16, 0, None, 0, 0, L.F32, L.LAYOUT_BLC, L.stream())
+    for _ in range(5):
+        fn()
+    evs = []
+    for _ in range(50):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    gpu_us = statistics.median(a.elapsed_time(b) for a, b in evs) * 1e3
+    return {"cpu_oracle_port_us": cpu_us, "cpu_threads": O.num_threads(), "ntx_gpu_us": gpu_us, "points": 4096,
+            "note": "grid_encode forward, L=4 T=2^14 F=2 fp32 table, median of 50; the CPU arm is the oracle port (no reference CPU path exists)"}
 
 
 def bench_cfg2(torch, L, field, device, peaks):

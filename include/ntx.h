@@ -181,6 +181,11 @@ int ntx_ngp_field_forward(const float* xyz, const float* dirs, const float* delt
  *   walk_budget: 0 = the reference's iteration structure.  > 0: after the first iteration a ray that has crossed this many empty
  *     voxels in one march without filling its n_step slots pauses (sentinel (0, -t), see raymarch.cu) and carries on in the next
  *     iteration from exactly that t: same samples, same image, but a launch no longer lasts as long as its longest walk.
+ *     With walk_budget > 0 and an occupancy mip the mip is consulted once per ray before the loop: rays that cannot reach an occupied
+ *     cell start dead (they would emit nothing and be dropped by the first composite_rays) and the others' `far` is shortened to the
+ *     end of their last maybe-occupied stretch; wide schedules (max_n_step > 8) round n_step down to a multiple of 4.
+ *     A ray that never pauses may then take up to max_steps + pause allowance samples where the reference truncates at max_steps
+ *     (only reachable when a ray crosses more than max_steps occupied lattice points); pass walk_budget = 0 where that cap matters.
  *   rays_o, rays_d [N,3] f32; aabb [6] f32 (device); grid = density bit-field; occupancy_mip nullable (ntx_build_occupancy_mip)
  *   weights_sum [N], depth [N], image [N,3] f32: overwritten (image WITHOUT the background term, like composite_rays)
  *   workspace: ntx_render_rays_workspace_bytes(N, sample_budget) bytes of device memory, 256-byte aligned
@@ -190,7 +195,8 @@ int ntx_ngp_field_forward(const float* xyz, const float* dirs, const float* delt
  *   kernel_ms_out: nullable host pointer to 2 floats.  When given, every march and field launch of the frame is bracketed by
  *     CUDA events on `stream`, the call synchronises the stream at the end and returns [0] the summed march-kernel time and
  *     [1] the summed field-kernel time in ms (bench.py's roofline; costs a few event records, do not use in production).
- * Not re-entrant (uses one set of events per device). */
+ * The call waits on its own run-ahead events (the ABI's one exception to "does not synchronise") and serialises concurrent callers
+ * on the same device with a per-device mutex (its events are per-device state); calls on different devices do not interact. */
 size_t ntx_render_rays_workspace_bytes(uint32_t N, uint32_t sample_budget);
 int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const float* aabb, float min_near, float bound,
                     float dt_gamma, uint32_t max_steps, uint32_t perturb, uint32_t sample_budget, uint32_t max_n_step,

@@ -71,7 +71,7 @@ __host__ __device__ inline FieldPlan field_plan(uint32_t L, uint32_t ns, uint32_
     p.a0_off = (p.wc_off + p.wc_bytes + 127u) & ~127u;
     p.lv_off = p.a0_off + kStages * p.a0_stage;
     p.misc_off = p.lv_off + (uint32_t)sizeof(PairLevel) * kFieldMaxLevels;
-    p.total = p.misc_off + 128u;
+    p.total = p.misc_off + 512u;      // barriers + TMEM slot (128 B) | per-stage MMA parameter table (384 B)
     return p;
 }
 
@@ -110,23 +110,43 @@ __device__ __forceinline__ void field_hidden_epilogue(uint32_t acc, uint32_t opn
 //   st = ns+1       h [128 x 32] . Wc0^T  -> 64      hidden epilogue
 //   st = ns+2..ns+nc                      -> 64      hidden epilogue
 //   st = ns+nc+1    h . Wc_out^T          -> 16      rgb
-__device__ __forceinline__ void issue_layer_tmem(uint32_t tmem_a, uint32_t w_smem, uint32_t Kdim, uint32_t N, uint32_t tmem_d) {
-    const uint32_t idesc = tc::idesc_f16_f32(kTileRows, N);
-    for (uint32_t ks = 0; ks < (Kdim >> 4); ks++) {
-        const uint64_t db = tc::smem_desc_kmajor_noswz(w_smem + ks * 256u, 128u, Kdim * 16u);
-        tc::mma_f16_ts(tmem_d, tmem_a + ks * 8u, db, idesc, ks > 0 ? 1u : 0u);     // 8 operand columns per K = 16 step
+// Everything the issuing lane needs for the MMAs of stage st (1 .. ns+nc+1), precomputed once per CTA: between the consumers' barrier
+// and the first UTCHMMA of a stage the round-2 build spent ~50 uniform-datapath instructions assembling descriptors (SASS) — on the
+// critical path of every stage, issued by one warp while the other three wait, next to twelve gathering warps.
+struct StageMma {
+    uint32_t b_lo[4];      // low words of the weight (B operand) descriptors of the K = 16 steps
+    uint32_t b_hi;         // their common high word (SBO, descriptor version)
+    uint32_t idesc;        // instruction descriptor (M = 128, N = 64 or 16)
+    uint32_t ksteps;       // 2 (the colour net's 32-wide input) or 4
+    uint32_t pad;
+};
+static_assert(sizeof(StageMma) == 32, "StageMma is two 16-byte loads");
+__device__ __forceinline__ StageMma make_stage_mma(uint32_t st, uint32_t ns, uint32_t nc, uint32_t K0, uint32_t ws_addr, uint32_t wc_addr) {
+    uint32_t w, Kdim, N;
+    if (st <= ns) { w = ws_addr + kFW * K0 * 2u + (st - 1) * (kFW * kFW * 2u); Kdim = kFW; N = st == ns ? 16u : (uint32_t)kFW; }
+    else if (st == ns + 1) { w = wc_addr; Kdim = kColorIn; N = kFW; }
+    else { w = wc_addr + kFW * kColorIn * 2u + (st - ns - 2) * (kFW * kFW * 2u); Kdim = kFW; N = st == ns + nc + 1 ? 16u : (uint32_t)kFW; }
+    StageMma m;
+    m.ksteps = Kdim >> 4;
+    m.idesc = tc::idesc_f16_f32(kTileRows, N);
+    m.b_hi = 0; m.pad = 0;
+    for (uint32_t ks = 0; ks < 4; ks++) {
+        const uint64_t d = tc::smem_desc_kmajor_noswz(w + (ks < m.ksteps ? ks : 0u) * 256u, 128u, Kdim * 16u);
+        m.b_lo[ks] = (uint32_t)d;
+        m.b_hi = (uint32_t)(d >> 32);
     }
+    return m;
 }
-__device__ __forceinline__ void field_issue_stage(uint32_t st, uint32_t ns, uint32_t nc, uint32_t K0, uint32_t tmem_a, uint32_t ws_addr, uint32_t wc_addr,
-                                                  uint32_t tmem_acc) {
-    if (st <= ns) {
-        const uint32_t w = ws_addr + kFW * K0 * 2u + (st - 1) * (kFW * kFW * 2u);
-        issue_layer_tmem(tmem_a, w, kFW, st == ns ? 16u : (uint32_t)kFW, tmem_acc);
-    } else if (st == ns + 1) {
-        issue_layer_tmem(tmem_a, wc_addr, kColorIn, kFW, tmem_acc);
-    } else {
-        const uint32_t w = wc_addr + kFW * kColorIn * 2u + (st - ns - 2) * (kFW * kFW * 2u);
-        issue_layer_tmem(tmem_a, w, kFW, st == ns + nc + 1 ? 16u : (uint32_t)kFW, tmem_acc);
+// issue stage st from its table entry: A = the operand columns in tensor memory (8 per K = 16 step)
+__device__ __forceinline__ void field_issue_stage(const StageMma* __restrict__ table, uint32_t st, uint32_t tmem_a, uint32_t tmem_acc) {
+    const uint4 lo = *reinterpret_cast<const uint4*>(table[st].b_lo);
+    const uint4 meta = *reinterpret_cast<const uint4*>(&table[st].b_hi);        // b_hi, idesc, ksteps, pad
+    const uint64_t hi = (uint64_t)meta.x << 32;
+    tc::mma_f16_ts(tmem_acc, tmem_a, hi | lo.x, meta.y, 0u);
+    tc::mma_f16_ts(tmem_acc, tmem_a + 8u, hi | lo.y, meta.y, 1u);
+    if (meta.z == 4u) {
+        tc::mma_f16_ts(tmem_acc, tmem_a + 16u, hi | lo.z, meta.y, 1u);
+        tc::mma_f16_ts(tmem_acc, tmem_a + 24u, hi | lo.w, meta.y, 1u);
     }
 }
 
@@ -183,6 +203,7 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
     uint64_t* empty_bar = full_bar + kStages;                                      // [kStages] consumer (MMA completion) -> producers
     uint64_t* mma_bar = empty_bar + kStages;                                       // [kCtx] layer done -> consumer warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + kCtx);
+    StageMma* stage_table = reinterpret_cast<StageMma*>(smem + plan.misc_off + 128u);   // [ns + nc + 2] (entry 0 unused)
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t K0 = plan.k0;
@@ -194,6 +215,7 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
         tc::fence_mbar_init();
     }
     if (warp == 0) tc::tmem_alloc<kFieldTmemCols>(tmem_slot);
+    if (tid >= 32 && tid < 32 + ns + nc + 2 && tid > 32) stage_table[tid - 32] = make_stage_mma(tid - 32, ns, nc, plan.k0, tc::smem_u32(ws_smem), tc::smem_u32(wc_smem));
     if (tid < L) lv[tid] = make_pair_level(make_level<3>(offsets, tid, S, H, /*gridtype=*/0, align), table);
     {
         const __half* w = w_sigma; uint8_t* dst = ws_smem;
@@ -407,7 +429,7 @@ __global__ void __launch_bounds__(kFieldThreads, 2) ngp_field_kernel(
                     tc::tmem_wait_st(); tc::tc_fence_before_sync(); consumer_sync();
                     if (st + 1 < nst && warp == 0 && tc::elect_one()) {
                         tc::tc_fence_after_sync();
-                        field_issue_stage(st + 1, ns, nc, K0, opnd_all, ws_addr, wc_addr, acc_all);
+                        field_issue_stage(stage_table, st + 1, opnd_all, acc_all);
                         tc::mma_commit(&mma_bar[c]);
                     }
                     PROBE_MARK(2)

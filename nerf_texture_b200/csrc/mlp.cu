@@ -54,15 +54,13 @@ __device__ __forceinline__ void issue_layer_chunked(uint32_t a_smem, uint32_t w_
         tc::mma_f16_ss(tmem_d, da, db, idesc, ks > 0 ? 1u : 0u);
     }
 }
-// D[128 x N] = A[128 x Kdim](tensor memory, 8 columns per K=16 step) . W[N x Kdim]^T
+// D[128 x N] = A[128 x Kdim](tensor memory, 8 columns per K=16 step) . W[N x Kdim]^T.  The weight descriptor of K step ks is the first
+// one + 16 * ks in its address field (256 bytes >> 4): one add per MMA on the issuing lane instead of a descriptor build.
 __device__ __forceinline__ void issue_layer_tmem(uint32_t tmem_a, uint32_t w_smem, uint32_t Kdim, uint32_t N, uint32_t tmem_d) {
     const uint32_t idesc = tc::idesc_f16_f32(kTileRows, N);
-    for (uint32_t ks = 0; ks < (Kdim >> 4); ks++) {
-        const uint64_t db = tc::smem_desc_kmajor_noswz(w_smem + ks * 256u, 128u, Kdim * 16u);
-        tc::mma_f16_ts(tmem_d, tmem_a + ks * 8u, db, idesc, ks > 0 ? 1u : 0u);
-    }
+    const uint64_t db0 = tc::smem_desc_kmajor_noswz(w_smem, 128u, Kdim * 16u);
+    for (uint32_t ks = 0; ks < (Kdim >> 4); ks++) tc::mma_f16_ts(tmem_d, tmem_a + ks * 8u, db0 + (uint64_t)(ks * 16u), idesc, ks > 0 ? 1u : 0u);
 }
-
 
 // one pass of a hidden-layer epilogue: NCOL fp32 accumulator columns of this thread's row -> activation -> fp16 ->
 // NCOL/2 operand columns in tensor memory (+ the training copy of the activations in global memory)

@@ -119,3 +119,30 @@ def test_paused_rays_cross_a_long_gap_between_two_objects():
                 np.testing.assert_array_equal(out[k].cpu().numpy(), ref[k].cpu().numpy(), err_msg="%s %s %d" % (k, sched, wb))
     # both balls are really seen: some rays accumulate samples from two separate stretches
     assert float(ref["weights_sum"].max()) > 0
+
+
+@pytest.mark.parametrize("world,tile,hw", [(2, 1024, (96, 96)), (8, 64, (57, 41)), (4, 1024, (64, 64))], ids=["2x1024", "8x64_ragged", "4x1024_fewer_tiles_than_ranks"])
+def test_sharded_frame_assembly_equals_whole_frame(world, tile, hw):
+    """BASELINE config 4 on one GPU: every rank's shard (interleaved tiles, render.shard_indices) is rendered straight into its planar
+    send block, the blocks are concatenated the way all_gather_into_tensor lays them out, and ntx_unshard_frame (un-permute + background
+    term) must reproduce the whole-frame render bit for bit — rays are independent, so sharding cannot change a pixel."""
+    L_ = ntx()
+    render, field, rays_o, rays_d, bits = _scene(hw, 1, 128, 1.0)
+    N = rays_o.shape[0]
+    whole = render.render_rays(field, rays_o, rays_d, bits, 1, 128, bg_color=0.25)
+    idxs, n_max, _ = render._shard_plan(N, world, tile, torch.device(DEV))
+    blocks = []
+    for r in range(world):
+        idx = idxs[r]
+        if idx.numel() == 0:                                  # more ranks than tiles: an empty shard sends zeros
+            blocks.append(torch.zeros(5 * n_max, device=DEV))
+            continue
+        out = render.render_rays(field, rays_o[idx].contiguous(), rays_d[idx].contiguous(), bits, 1, 128, block_rows=n_max)
+        assert out["block"].numel() == 5 * n_max
+        blocks.append(out["block"])
+    gathered = torch.cat(blocks).contiguous()
+    image = torch.empty(N, 3, device=DEV); depth = torch.empty(N, device=DEV); wsum = torch.empty(N, device=DEV)
+    L_.call("ntx_unshard_frame", L_.ptr(gathered), world, n_max, tile, N, 0.25, L_.ptr(image), L_.ptr(depth), L_.ptr(wsum), L_.stream())
+    torch.cuda.synchronize()
+    for got, k in ((image, "image"), (depth, "depth"), (wsum, "weights_sum")):
+        np.testing.assert_array_equal(got.cpu().numpy(), whole[k].cpu().numpy(), err_msg=k)
