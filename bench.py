@@ -203,6 +203,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     W, K = max(args.warmup, 3), args.steps
+    # host side of the rank on the GPU's own NUMA node (pinned staging buffers, frame mailbox, launches); undone for the CPU baseline
+    prev_affinity = L.bind_host_thread_to_gpu(local_rank)
     L.lib()
     assert L.lib().ntx_device_ok() == 1, "libntx needs a CC 10.x device"
 
@@ -289,7 +291,8 @@ def main():
                    "field": "hashgrid L=16 T=2^19 F=2 fp16 -> FFMLP(32,16,64,2) -> SH4 -> FFMLP(32,3,64,3)", "rays": N, "samples_per_frame": samples_per_frame,
                    "loop_iterations": iterations, "sample_schedule": "n_step = clamp(32N // n_alive, 1, 256) rounded to 4, walk budget %d, rays that cannot reach an occupied cell dropped before the first march (same image as the reference's clamp(N // n_alive, 1, 8): 43 iterations)" % render.WALK_BUDGET,
                    "max_steps": 1024, "dt_gamma": 0, "occupancy": "ball r=0.5, H=128, 1 cascade (its occupancy mip is built once and cached per bit-field version, like the drop-in march_rays)",
-                   "l2": "flushed between timed steps (256 MiB memset)", "parallelism": "ray-sharded x%d" % world},
+                   "l2": "flushed between timed steps (256 MiB memset)", "parallelism": "ray-sharded x%d" % world,
+                   "host": "rank thread bound to the GPU's NUMA node (NVML ideal affinity)" if prev_affinity else "no NUMA binding (NVML unavailable)"},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
 
@@ -343,7 +346,9 @@ def main():
                             "tensor_note": "36864 FLOP/sample on tcgen05: %.1f TFLOP/s achieved inside the kernel" % (live * 36864 / kt / 1e12)}
         # ---- BASELINE config 1: grid_encode forward L=4 T=2^14 F=2 on 4096 random points — the reference has no CPU path, so
         #      the "CPU" number is the oracle port on the host cores; the GPU kernel on the same input next to it
-        line["cfg1"] = bench_cfg1(torch, L, device)
+        if prev_affinity:
+            os.sched_setaffinity(0, prev_affinity)              # CPU legs (cfg1 here, cpu_baseline below) use every host core; the GPU
+        line["cfg1"] = bench_cfg1(torch, L, device)             # side measurements that follow are device-timed
         # ---- BASELINE config 2: 2^20 samples through the fused field kernel and the stand-alone encoder ------------
         line["cfg2"] = bench_cfg2(torch, L, field, device, peaks)
         # ---- the reference's own CUDA kernels (rebuilt for sm_100a, oracle/_ref) on the same frame, when the build is present:
@@ -363,6 +368,8 @@ def main():
             # ---- BASELINE config 5: training step (grid + sigma-MLP forward/backward on 2^18 samples) through the operator API
             line["cfg5"] = run_tool("bench_cfg5.py", [["--backend", "ntx"], ["--backend", "ref"]], ("ntx", "reference_cuda"), "step_ms")
         if not args.no_cpu_baseline and world == 1:
+            if prev_affinity:
+                os.sched_setaffinity(0, prev_affinity)          # the CPU arm uses every host core again
             v, dt, ns, cores, sample = cpu_render_sample(stride=5)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "seconds": dt}
     if rank == 0:

@@ -134,3 +134,19 @@ def workspace(kind, nbytes, device):
         ws = torch.zeros(max(int(nbytes), 4096), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
+
+
+def bind_host_thread_to_gpu(device_index):
+    """Pin the calling thread (and what it allocates next: pinned staging buffers, the frame mailbox) to the CPUs of the NUMA node the
+    GPU hangs off (NVML's ideal CPU affinity).  On a two-socket B200 box a rank whose pinned buffers live on the far socket pays for it
+    in every host<->device copy and every mailbox read; returns the previous affinity (for os.sched_setaffinity) or None if NVML is
+    not available.  Best effort: never raises."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        prev = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(int(device_index)))
+        return prev
+    except Exception:
+        return None
