@@ -217,12 +217,29 @@ def main():
         my_o, my_d = rays_o, rays_d
 
     n_max = render._shard_plan(N, world, 1024, device)[1] if world > 1 else None
+    # config 4's exchange step: NVLink peer reads fused into the assembly kernel when symmetric memory is available (NTX_EXCHANGE=nccl
+    # forces the all-gather), else ONE NCCL all_gather + the assembly kernel
+    exchange = render.PeerFrameExchange.create(N, device=device) if (world > 1 and os.environ.get("NTX_EXCHANGE", "peer") != "nccl") else None
+    if world > 1:
+        flag = torch.tensor([1 if exchange is not None else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)                     # all ranks or none
+        if int(flag.item()) == 0:
+            exchange = None
+
+    def finish(out):
+        if world == 1:
+            return out
+        if exchange is not None:
+            res = exchange.assemble(1.0)
+            res["iterations"] = out["iterations"]
+            return res
+        return render.gather_frame(out, N)
 
     def step_device():
-        # this rank's (resident) shard of the frame, rendered straight into its planar send block, + the tile all-gather and the
-        # assembly kernel (config 4); one GPU: the frame
-        out = render.render_rays(field, my_o, my_d, bits, 1, 128, block_rows=n_max, cache_mip=True)
-        return render.gather_frame(out, N) if world > 1 else out
+        # this rank's (resident) shard of the frame, rendered straight into its planar send block, + the exchange and the assembly
+        # kernel (config 4); one GPU: the frame
+        out = render.render_rays(field, my_o, my_d, bits, 1, 128, block_rows=n_max, cache_mip=True, block_out=exchange.block() if exchange is not None else None)
+        return finish(out)
 
     def barrier():
         if world > 1:
@@ -272,9 +289,9 @@ def main():
 
     def step_e2e():
         d_o.copy_(h_o, non_blocking=True); d_d.copy_(h_d, non_blocking=True)
-        out = render.render_rays(field, d_o, d_d, bits, 1, 128, block_rows=n_max, cache_mip=True)       # each rank uploads and renders its own shard
-        if world > 1:
-            out = render.gather_frame(out, N)
+        out = render.render_rays(field, d_o, d_d, bits, 1, 128, block_rows=n_max, cache_mip=True,       # each rank uploads and renders its own shard
+                                 block_out=exchange.block() if exchange is not None else None)
+        out = finish(out)
         if rank == 0:
             h_img.copy_(out["image"], non_blocking=True); h_dep.copy_(out["depth"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -287,7 +304,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": "render_1024x1024_network_ff_random_weights (BASELINE config 3%s)" % ("; rays sharded in interleaved 1024-ray tiles + one NCCL all_gather, config 4" if world > 1 else ""),
+        "config": {"workload": "render_1024x1024_network_ff_random_weights (BASELINE config 3%s)" % (("; rays sharded in interleaved 1024-ray tiles + " + ("NVLink peer reads fused into the assembly kernel (symmetric memory)" if exchange is not None else "one NCCL all_gather") + ", config 4") if world > 1 else ""),
                    "field": "hashgrid L=16 T=2^19 F=2 fp16 -> FFMLP(32,16,64,2) -> SH4 -> FFMLP(32,3,64,3)", "rays": N, "samples_per_frame": samples_per_frame,
                    "loop_iterations": iterations, "sample_schedule": "n_step = clamp(32N // n_alive, 1, 256) rounded to 4, walk budget %d, rays that cannot reach an occupied cell dropped before the first march (same image as the reference's clamp(N // n_alive, 1, 8): 43 iterations)" % render.WALK_BUDGET,
                    "max_steps": 1024, "dt_gamma": 0, "occupancy": "ball r=0.5, H=128, 1 cascade (its occupancy mip is built once and cached per bit-field version, like the drop-in march_rays)",
@@ -303,9 +320,9 @@ def main():
         barrier()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         ev[0].record()
-        o = render.render_rays(field, my_o, my_d, bits, 1, 128, time_kernels=True, block_rows=n_max)
+        o = render.render_rays(field, my_o, my_d, bits, 1, 128, time_kernels=True, block_rows=n_max, block_out=exchange.block() if exchange is not None else None)
         ev[1].record()
-        render.gather_frame(o, N)
+        finish(o)
         ev[2].record()
         torch.cuda.synchronize()
         mine = torch.tensor([o["march_ms"], o["field_ms"], ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), float(o["iterations"])], dtype=torch.float32, device=device)

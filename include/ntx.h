@@ -214,6 +214,14 @@ int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_t N, const 
 int ntx_unshard_frame(const float* gathered, uint32_t world, uint32_t n_max, uint32_t tile, uint32_t N, float bg,
                       float* image, float* depth, float* weights_sum, ntx_stream_t stream);
 
+/* The same epilogue fused with the exchange: `peers_dev` is a DEVICE array of `world` pointers, entry r = this rank's NVLink mapping of
+ * rank r's planar block buffer (symmetric memory: cudaIpc / torch.distributed._symmetric_memory buffer_ptrs_dev); the block of this
+ * frame starts `offset_floats` into each buffer.  The kernel reads the peers' blocks in place while it un-permutes — no all-gather, no
+ * staging copy.  The caller must order it after a cross-rank barrier (all blocks written) and must not overwrite a block before every
+ * rank has passed the next barrier (double-buffer the blocks). */
+int ntx_unshard_frame_peers(const void* peers_dev, size_t offset_floats, uint32_t world, uint32_t n_max, uint32_t tile,
+                            uint32_t N, float bg, float* image, float* depth, float* weights_sum, ntx_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------ density-grid maintenance
  * The density-grid half of NeRFRenderer.update_extra_state (nerf/renderer.py:567-647) as one launch chain, no host round trip:
  *   tmp_grid = -1; for every cascade: query sigma * density_scale at the grid cells (positions generated in the kernel from the

@@ -45,6 +45,7 @@ _SIGS = {
     "ntx_render_rays": [_vp, _vp, _u32, _vp, _f32, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _u32, _f32, _u32, _int, _vp, _vp, _f32,
                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ntx_unshard_frame": [_vp, _u32, _u32, _u32, _u32, _f32, _vp, _vp, _vp, _vp],
+    "ntx_unshard_frame_peers": [_vp, _sz, _u32, _u32, _u32, _u32, _f32, _vp, _vp, _vp, _vp],
     "ntx_update_density_grid": [_vp, _vp, _u32, _u32, _f32, _f32, _f32, _f32, _vp, _vp, _u32, _f32, _u32, _int, _vp, _vp, _u32, _vp, _int, _vp, _vp, _vp],
 }
 _SIZE_FNS = {

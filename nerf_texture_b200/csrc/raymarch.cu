@@ -1609,6 +1609,37 @@ __global__ void __launch_bounds__(256) unshard_frame_kernel(const float* __restr
 }
 }  // namespace ntx
 
+// The same assembly without the collective: every rank's planar block lives in NVLink-mapped symmetric memory, and this kernel READS
+// the other ranks' blocks in place (ld.global on peer addresses) while it un-permutes — exchange, un-permute and background term in
+// one kernel, 20 B per ray over NVLink, no staging copy.  `peers` = device array of `world` base pointers (this rank's view of every
+// rank's buffer, e.g. torch.distributed._symmetric_memory's buffer_ptrs_dev); the caller orders it after a cross-rank barrier.
+namespace ntx {
+__global__ void __launch_bounds__(256) unshard_frame_peers_kernel(const float* const* __restrict__ peers, const size_t offset_floats, const uint32_t world,
+                                                                  const uint32_t n_max, const uint32_t tile, const uint32_t N, const float bg,
+                                                                  float* __restrict__ image, float* __restrict__ depth, float* __restrict__ weights_sum) {
+    const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= N) return;
+    const uint32_t k = ray / tile, rank = k % world, j = (k / world) * tile + (ray - k * tile);
+    const float* blk = peers[rank] + offset_floats;
+    const float ws = blk[j];
+    weights_sum[ray] = ws;
+    depth[ray] = blk[n_max + j];
+    const float b = __fmul_rn(__fsub_rn(1.0f, ws), bg);
+    const float* c = blk + 2u * (size_t)n_max + 3u * (size_t)j;
+    image[(size_t)ray * 3] = __fadd_rn(c[0], b); image[(size_t)ray * 3 + 1] = __fadd_rn(c[1], b); image[(size_t)ray * 3 + 2] = __fadd_rn(c[2], b);
+}
+}  // namespace ntx
+
+extern "C" int ntx_unshard_frame_peers(const void* peers_dev, size_t offset_floats, uint32_t world, uint32_t n_max, uint32_t tile, uint32_t N, float bg,
+                                       float* image, float* depth, float* weights_sum, ntx_stream_t stream) {
+    NTX_REQUIRE(peers_dev && image && depth && weights_sum, NTX_ERR_INVALID_ARGUMENT, "unshard_frame_peers: null pointer");
+    NTX_REQUIRE(world >= 1 && tile >= 1 && n_max >= 1, NTX_ERR_INVALID_ARGUMENT, "unshard_frame_peers: bad world / tile / n_max");
+    if (N == 0) return NTX_OK;
+    unshard_frame_peers_kernel<<<ceil_div<uint32_t>(N, 256), 256, 0, ST(stream)>>>(static_cast<const float* const*>(peers_dev), offset_floats, world, n_max, tile, N, bg,
+                                                                                   image, depth, weights_sum);
+    return check_launch("unshard_frame_peers");
+}
+
 extern "C" int ntx_unshard_frame(const float* gathered, uint32_t world, uint32_t n_max, uint32_t tile, uint32_t N, float bg, float* image, float* depth,
                                  float* weights_sum, ntx_stream_t stream) {
     NTX_REQUIRE(gathered && image && depth && weights_sum, NTX_ERR_INVALID_ARGUMENT, "unshard_frame: null pointer");

@@ -124,7 +124,7 @@ def _aabb_tensor(bound, dev, cache={}):
 
 
 def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aabb=None, min_near=0.2, dt_gamma=0.0, max_steps=1024, bg_color=1.0,
-                perturb=0, count_samples=False, profile=None, use_mip=True, device_loop=True, mip=None, schedule="auto", time_kernels=False, block_rows=None, cache_mip=False):
+                perturb=0, count_samples=False, profile=None, use_mip=True, device_loop=True, mip=None, schedule="auto", time_kernels=False, block_rows=None, cache_mip=False, block_out=None):
     """Inference branch of NeRFRenderer.run_cuda (renderer.py:436-489).  rays_o/d [N,3] fp32 CUDA.
     Returns dict(image [N,3], depth [N], weights_sum [N], iterations, n_samples (if count_samples)).
     device_loop=True (default): the whole loop is ONE libntx call whose iteration state stays on the device (ntx_render_rays);
@@ -168,7 +168,8 @@ def render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, aab
         # the raw result as ONE planar block [weights_sum (n) | depth (n) | rgb (3n)]: what a rank sends in the sharded path, and what
         # the fused epilogue (ntx_unshard_frame: un-permute + background term) reads
         n_blk = N if block_rows is None else int(block_rows)
-        block = torch.empty(5 * n_blk, dtype=torch.float32, device=dev)
+        block = torch.empty(5 * n_blk, dtype=torch.float32, device=dev) if block_out is None else block_out    # block_out: e.g. a slice of symmetric memory
+        assert block.numel() == 5 * n_blk and block.dtype == torch.float32 and block.is_contiguous()
         wsum_c, depth_c, image_c = block[:N], block[n_blk:n_blk + N], block[2 * n_blk:2 * n_blk + 3 * N].view(N, 3)
         if count_samples:
             counter.zero_()
@@ -282,6 +283,58 @@ def _shard_plan(N, world, tile, device):
     return plan
 
 
+class PeerFrameExchange:
+    """The sharded frame's exchange step over NVLink peer memory instead of a collective ("fused op <-> collective adjacency").
+    Every rank renders its shard straight into its slice of a SYMMETRIC buffer (torch.distributed._symmetric_memory: each rank's
+    allocation is mapped into every other rank's address space over NVLink / NVSwitch); after one device-side cross-rank barrier
+    `ntx_unshard_frame_peers` reads all ranks' blocks in place while it puts every ray at its image position and adds the background
+    term: exchange + un-permute + epilogue in ONE kernel, no all-gather, no staging copy.  Blocks are double-buffered: a rank may only
+    overwrite a block two frames later, after everybody has passed the next frame's barrier.
+    `PeerFrameExchange.create(...)` returns None where symmetric memory is not available (then gather_frame's NCCL all-gather is used)."""
+
+    def __init__(self, hdl, buf, n_max, world, rank, tile, N):
+        self.hdl, self.buf, self.n_max, self.world, self.rank, self.tile, self.N, self.frame = hdl, buf, n_max, world, rank, tile, N, 0
+
+    @classmethod
+    def create(cls, N, group=None, tile=1024, device=None):
+        import torch.distributed as dist
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            group = group or dist.group.WORLD
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+            n_max = _shard_plan(N, world, tile, torch.device("cpu"))[1]
+            if hasattr(symm_mem, "enable_symm_mem_for_group"):
+                try:
+                    symm_mem.enable_symm_mem_for_group(group.group_name)
+                except Exception:
+                    pass
+            buf = symm_mem.empty(2 * 5 * n_max, dtype=torch.float32, device=device)
+            hdl = symm_mem.rendezvous(buf, group)
+            if hdl.world_size != world or not hdl.buffer_ptrs_dev:
+                return None
+            return cls(hdl, buf, n_max, world, rank, tile, N)
+        except Exception:
+            return None
+
+    def block(self):
+        """this frame's send block of this rank (render_rays(..., block_rows=n_max, block_out=exchange.block()))"""
+        h = self.frame & 1
+        return self.buf[h * 5 * self.n_max:(h + 1) * 5 * self.n_max]
+
+    def assemble(self, bg_color=1.0):
+        """barrier (all blocks of this frame written) + the fused exchange / un-permute / background kernel; returns image, depth, weights_sum"""
+        dev = self.buf.device
+        h = self.frame & 1
+        self.hdl.barrier(channel=h)
+        image = torch.empty(self.N, 3, dtype=torch.float32, device=dev)
+        depth = torch.empty(self.N, dtype=torch.float32, device=dev)
+        wsum = torch.empty(self.N, dtype=torch.float32, device=dev)
+        L.call("ntx_unshard_frame_peers", int(self.hdl.buffer_ptrs_dev), h * 5 * self.n_max, self.world, self.n_max, self.tile, self.N, float(bg_color),
+               L.ptr(image), L.ptr(depth), L.ptr(wsum), L.stream())
+        self.frame += 1
+        return dict(image=image, depth=depth, weights_sum=wsum)
+
+
 def gather_frame(out, N, group=None, tile=1024, bg_color=1.0):
     """ONE all_gather of the per-rank planar result blocks (weights_sum | depth | rgb = 20 B/ray) + one kernel that puts every ray
     back at its image position and adds the background term (ntx_unshard_frame).
@@ -318,14 +371,20 @@ def gather_frame(out, N, group=None, tile=1024, bg_color=1.0):
     return res
 
 
-def render_image_sharded(field, rays_o, rays_d, density_bitfield, cascade, grid_size, group=None, tile=1024, bg_color=1.0, **kw):
-    """Each rank renders its interleaved tiles of the frame straight into its planar send block; ONE all_gather and one assembly
-    kernel follow.  rays_o/rays_d: the full frame's rays on every rank ([N,3], e.g. generated on-device from the pose)."""
+def render_image_sharded(field, rays_o, rays_d, density_bitfield, cascade, grid_size, group=None, tile=1024, bg_color=1.0, exchange=None, **kw):
+    """Each rank renders its interleaved tiles of the frame straight into its planar send block; then either ONE all_gather and one
+    assembly kernel (NCCL), or — with `exchange=PeerFrameExchange.create(N, group)` — one cross-rank barrier and one kernel that reads
+    the peers' blocks over NVLink while it assembles the image.  rays_o/rays_d: the full frame's rays on every rank ([N,3])."""
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return render_rays(field, rays_o, rays_d, density_bitfield, cascade, grid_size, bg_color=bg_color, **kw)
     N = rays_o.shape[0]
     idxs, n_max, _ = _shard_plan(N, dist.get_world_size(group), tile, rays_o.device)
     idx = idxs[dist.get_rank(group)]
+    if exchange is not None:
+        out = render_rays(field, rays_o[idx], rays_d[idx], density_bitfield, cascade, grid_size, block_rows=n_max, block_out=exchange.block(), **kw)
+        res = exchange.assemble(bg_color)
+        res["iterations"] = out["iterations"]
+        return res
     out = render_rays(field, rays_o[idx], rays_d[idx], density_bitfield, cascade, grid_size, block_rows=n_max, **kw)
     return gather_frame(out, N, group, tile, bg_color=bg_color)

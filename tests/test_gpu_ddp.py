@@ -83,3 +83,49 @@ def test_two_gpu_data_parallel_step_nccl():
     outs = [p.communicate(timeout=600) for p in procs]
     for r, (so, se) in enumerate(outs):
         assert "RANK%d OK" % r in so, (so[-3000:], se[-3000:])
+
+
+FRAME_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from nerf_texture_b200 import render, scene
+rank = int(os.environ["RANK"])
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", rank=rank, world_size=2, device_id=dev)
+field = render.NGPField.random(dev, seed=0)
+H = 96
+rays_o, rays_d = scene.pinhole_rays(H, H, dev)
+bits = scene.ball_bitfield(1, 128, 1.0, dev)
+N = rays_o.shape[0]
+whole = render.render_rays(field, rays_o, rays_d, bits, 1, 128, bg_color=0.5)
+ok = True
+nccl = render.render_image_sharded(field, rays_o, rays_d, bits, 1, 128, tile=256, bg_color=0.5)
+ok = ok and all(torch.equal(nccl[k], whole[k]) for k in ("image", "depth", "weights_sum"))
+ex = render.PeerFrameExchange.create(N, tile=256, device=dev)
+flag = torch.tensor([1 if ex is not None else 0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if int(flag.item()) == 1:
+    for frame in range(4):                                    # four frames: both halves of the double buffer, twice
+        peer = render.render_image_sharded(field, rays_o, rays_d, bits, 1, 128, tile=256, bg_color=0.5, exchange=ex)
+        ok = ok and all(torch.equal(peer[k], whole[k]) for k in ("image", "depth", "weights_sum"))
+    print("RANK%%d PEER" %% rank)
+else:
+    print("RANK%%d NOPEER" %% rank)
+torch.cuda.synchronize()
+print("RANK%%d %%s" %% (rank, "OK" if ok else "MISMATCH"))
+dist.destroy_process_group()
+""" % ROOT
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_two_gpu_sharded_frame_nccl_and_peer_exchange():
+    """BASELINE config 4 on two real GPUs: the ray-sharded frame assembled (a) after ONE NCCL all-gather and (b) by the kernel that reads
+    the peers' blocks over NVLink (symmetric memory) must both equal the whole-frame render bit for bit, frame after frame."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, "-c", FRAME_WORKER], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    for r, (so, se) in enumerate(outs):
+        assert "RANK%d OK" % r in so, (so[-3000:], se[-3000:])
+    print(outs[0][0][-200:])
