@@ -1508,7 +1508,8 @@ extern "C" int ntx_render_rays(const float* rays_o, const float* rays_d, uint32_
     const uint32_t pause_iters = walk_budget ? 2u * H * C / walk_budget + 2u : 0u;
     const uint32_t step_limit = max_steps + pause_iters * max_n_step, iter_limit = max_steps + pause_iters;
     // rays that cannot hit anything occupied start dead (see frame_init_kernel); not for the reference's exact iteration structure
-    const bool prekill = walk_budget != 0 && occupancy_mip != nullptr;
+    // (perturb != 0: the jitter of a ray is drawn from its slot number in the first march, raymarching.cu:1011 — slots must stay ray ids)
+    const bool prekill = walk_budget != 0 && occupancy_mip != nullptr && perturb == 0;
     // How many iterations the launching thread runs ahead of the one whose n_alive it has read.  1: grids shrink as soon as possible and
     // at most two empty iterations are queued at the end.  Queueing 3 ahead was measured on an 8-GPU box to check whether the host's
     // wake-up after each event limits a 1/8 shard: 1.45 -> 1.85 ms per frame — it does not; the extra empty launches and full-size
