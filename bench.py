@@ -384,6 +384,9 @@ def main():
                                                                  ["--backend", "ref", "--size", str(IMG), "--time", "5"]], ("ntx", "reference_cuda"), "frame_ms")
             # ---- BASELINE config 5: training step (grid + sigma-MLP forward/backward on 2^18 samples) through the operator API
             line["cfg5"] = run_tool("bench_cfg5.py", [["--backend", "ntx"], ["--backend", "ref"]], ("ntx", "reference_cuda"), "step_ms")
+            # ---- SURVEY 8 f3, the mesh front end of the texture field: MeshProjector.project on 2^20 samples — one fused kernel vs the
+            #      reference's unmodified torch chain on the drop-in frnn / RayTracer packages vs the CPU restatement
+            line["mesh"] = run_tool("bench_mesh.py", [[]], ("ntx",), "project_fused_ms").get("ntx")
         if not args.no_cpu_baseline and world == 1:
             if prev_affinity:
                 os.sched_setaffinity(0, prev_affinity)          # the CPU arm uses every host core again
@@ -406,6 +409,8 @@ def run_tool(tool, arg_sets, names, key):
             out[name] = json.loads(res[0][7:]) if res else {"unavailable": (r.stderr or r.stdout)[-300:]}
         except Exception as e:
             out[name] = {"unavailable": repr(e)[:200]}
+    if len(names) < 2:
+        return out
     a, b = out.get(names[0], {}), out.get(names[1], {})
     if key in a and key in b and a[key] > 0:
         out["speedup_vs_reference_cuda"] = b[key] / a[key]

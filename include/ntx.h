@@ -243,6 +243,44 @@ int ntx_update_density_grid(float* density_grid, uint8_t* density_bitfield, uint
                             const void* w_sigma_f16, const int* cells, uint32_t n_cells, const float* noise,
                             int force_full_grid, void* workspace, float* stats_out, ntx_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * Mesh front end of the texture field: what MeshProjector.project (tools/map.py:414-433) does per sample —
+ * K nearest mesh vertices (frnn.frnn_grid_points, tools/map.py:396,456) -> coarse normal (tools/map.py:454-500) -> two nearest-hit ray
+ * casts along +-normal (external/RayTracer) -> surface point, signed distance, face.
+ *
+ * ntx_mesh_create replaces `_raytracing.create_raytracer(vertices, triangles)` (external/RayTracer/src/bindings.cpp:17,
+ * src/raytracer.cu:21-41) AND the grid frnn builds on its first call (tools/map.py:396): HOST arrays `vertices` [n_vertices,3] f32 and
+ * `triangles` [n_triangles,3] i32 (n_triangles may be 0: neighbour queries only) -> an opaque handle that owns the two search trees on
+ * the CURRENT device.  Non-finite vertices and out-of-range indices -> NTX_ERR_INVALID_ARGUMENT.  Unlike the reference wrapper
+ * (raytracer.py:17-24) meshes of <= 8 triangles need no padding.  The call synchronises (cudaMalloc + cudaMemcpy), like the reference's.
+ * ntx_mesh_info: out6 = {n_vertices, n_triangles, triangle-tree nodes, its depth, vertex-tree nodes, its depth}. */
+int ntx_mesh_create(const float* vertices, uint32_t n_vertices, const int32_t* triangles, uint32_t n_triangles, void** mesh_out);
+int ntx_mesh_destroy(void* mesh);
+int ntx_mesh_info(const void* mesh, uint32_t* out6);
+
+/* `RayTracer::trace` (external/RayTracer/include/raytracing/raytracer.h:20, src/bvh.cu:695-721): for each ray the nearest triangle hit
+ * with 0 <= t < 10 (MAX_DIST, bvh.cu:36) by the formula of triangle.cuh:27-39.
+ *   rays_o, rays_d [N,3] f32 (device) -> depth [N] = t or 10, positions [N,3] = o + depth * d, normals [N,3] = unit face normal or 0,
+ *   face_idx [N] i64 = index into `triangles`; a MISS LEAVES face_idx UNTOUCHED (the reference's wrapper pre-fills -1, raytracer.py:37).
+ *   positions may alias rays_o and normals rays_d (the wrapper's inplace=True).
+ * The result is that of an exhaustive scan over the triangles in index order (ties in t: lowest index); every product and sum of the
+ * hit formula is rounded separately.  The reference's own binary may differ in the last bits where nvcc fused multiply-adds. */
+int ntx_mesh_trace(const void* mesh, const float* rays_o, const float* rays_d, float* positions, float* normals, float* depth,
+                   int64_t* face_idx, uint32_t N, ntx_stream_t stream);
+
+/* frnn.frnn_grid_points(queries[None], vertices[None], K=K, r=r, return_sorted=True) for one batch element: the K nearest mesh
+ * vertices with squared distance < r*r, ascending (ties: lowest index).  dists [N,K] f32 SQUARED distances, idxs [N,K] i64; both
+ * padded with -1 when fewer than K vertices are in range.  1 <= K <= 32. */
+int ntx_mesh_knn(const void* mesh, const float* queries, uint32_t N, uint32_t K, float r, float* dists, int64_t* idxs, ntx_stream_t stream);
+
+/* MeshProjector.project(xyz, K) up to its two torch one-liners on the outputs (tbn = self.tbn[face_idx], h_mask = |sdf| < threshold),
+ * fused into one kernel: per sample the K-neighbour list stays in registers, the coarse normal of knn(use_dir_vec=True,
+ * weighting='Shepard', dir_vec_wdist) is formed from `vertex_normals` [n_vertices,3] f32 (device) and both casts run back to back.
+ *   -> p_sur [N,3], sdf [N] (-depth_inner if depth_inner < depth_outer else depth_outer), normal [N,3], face_idx [N] i64 (-1: neither
+ *   cast hit anything within 10).  1 <= K <= 16; the mesh must have triangles. */
+int ntx_mesh_project(const void* mesh, const float* vertex_normals, const float* xyz, uint32_t N, uint32_t K, float r, float dir_vec_wdist,
+                     float* p_sur, float* sdf, float* normal, int64_t* face_idx, ntx_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,12 @@ _SIGS = {
                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ntx_unshard_frame": [_vp, _u32, _u32, _u32, _u32, _f32, _vp, _vp, _vp, _vp],
     "ntx_unshard_frame_peers": [_vp, _sz, _u32, _u32, _u32, _u32, _f32, _vp, _vp, _vp, _vp],
+    "ntx_mesh_create": [_vp, _u32, _vp, _u32, _vp],
+    "ntx_mesh_destroy": [_vp],
+    "ntx_mesh_info": [_vp, _vp],
+    "ntx_mesh_trace": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _vp],
+    "ntx_mesh_knn": [_vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp],
+    "ntx_mesh_project": [_vp, _vp, _vp, _u32, _u32, _f32, _f32, _vp, _vp, _vp, _vp, _vp],
     "ntx_update_density_grid": [_vp, _vp, _u32, _u32, _f32, _f32, _f32, _f32, _vp, _vp, _u32, _f32, _u32, _int, _vp, _vp, _u32, _vp, _int, _vp, _vp, _vp],
 }
 _SIZE_FNS = {
@@ -87,7 +93,7 @@ def check(rc):
 
 
 launches = 0  # number of libntx kernel-launching calls made by this process (bench.py reports the delta as gpu_launches)
-_NO_LAUNCH = {"ntx_allocate_splitk", "ntx_free_splitk"}
+_NO_LAUNCH = {"ntx_allocate_splitk", "ntx_free_splitk", "ntx_mesh_create", "ntx_mesh_destroy", "ntx_mesh_info"}
 
 
 def call(name, *args):

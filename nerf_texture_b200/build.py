@@ -19,7 +19,7 @@ LIBDIR = os.path.join(HERE, "lib")
 _TAG = os.environ.get("NTX_BUILD_TAG", "")
 OBJDIR = os.path.join(LIBDIR, "obj" + ("_" + _TAG if _TAG else ""))
 LIB = os.path.join(LIBDIR, "libntx" + ("_" + _TAG if _TAG else "") + ".so")
-SOURCES = ["api.cu", "grid.cu", "sh.cu", "raymarch.cu", "mlp.cu", "mlp_bwd.cu", "field.cu"]
+SOURCES = ["api.cu", "grid.cu", "sh.cu", "raymarch.cu", "mlp.cu", "mlp_bwd.cu", "field.cu", "mesh.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -16,7 +16,7 @@ _lib = None
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("ntx_oracle.c", "grid_impl.inc", "sh_table.inc")]
+    srcs = [os.path.join(_HERE, f) for f in ("ntx_oracle.c", "ntx_oracle_mesh.c", "grid_impl.inc", "sh_table.inc")]
     if (not force) and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
         return _SO
     r = subprocess.run(["make", "-C", _HERE, "libntx_oracle.so"], capture_output=True, text=True)
@@ -377,3 +377,35 @@ def render_rays(rays_o, rays_d, bitfield, cascade, grid_size, bound, embeddings_
         it += 1
     image = image + (1 - weights_sum)[:, None] * np.float32(bg_color)
     return image, depth, weights_sum, n_samples, it
+
+
+# ------------------------------------------------------------------------------------------------ mesh front end (ntx_oracle_mesh.c)
+def mesh_trace(vertices, triangles, rays_o, rays_d):
+    """external/RayTracer raytracer.py:31-68 `trace`: positions [N,3], face_normals [N,3], depth [N], face_idx [N] i64 (-1 = no hit)."""
+    v, t = _c(vertices, np.float32), _c(triangles, np.int32)
+    o, d = _c(rays_o, np.float32).reshape(-1, 3), _c(rays_d, np.float32).reshape(-1, 3)
+    N = o.shape[0]
+    pos, nrm, depth = np.empty((N, 3), np.float32), np.empty((N, 3), np.float32), np.empty(N, np.float32)
+    face = np.full(N, -1, np.int64)
+    lib().orc_mesh_trace(_p(v), _p(t), C.c_uint32(t.shape[0]), _p(o), _p(d), C.c_uint32(N), _p(pos), _p(nrm), _p(depth), _p(face))
+    return pos, nrm, depth, face
+
+
+def points_knn(points, queries, K, r):
+    """frnn.frnn_grid_points(queries, points, K=K, r=r, return_sorted=True) for one batch element: squared dists [N,K], idxs [N,K] i64."""
+    p, q = _c(points, np.float32), _c(queries, np.float32).reshape(-1, 3)
+    N = q.shape[0]
+    dists, idxs = np.empty((N, K), np.float32), np.empty((N, K), np.int64)
+    lib().orc_points_knn(_p(p), C.c_uint32(p.shape[0]), _p(q), C.c_uint32(N), C.c_uint32(K), C.c_float(r), _p(dists), _p(idxs))
+    return dists, idxs
+
+
+def mesh_project(vertices, vertex_normals, triangles, xyz, K=8, r=100.0, dir_vec_wdist=0.05):
+    """tools/map.py:414-433 MeshProjector.project: p_sur [N,3], sdf [N], normal [N,3], face_idx [N] i64."""
+    v, vn, t = _c(vertices, np.float32), _c(vertex_normals, np.float32), _c(triangles, np.int32)
+    x = _c(xyz, np.float32).reshape(-1, 3)
+    N = x.shape[0]
+    p_sur, sdf, normal, face = np.empty((N, 3), np.float32), np.empty(N, np.float32), np.empty((N, 3), np.float32), np.empty(N, np.int64)
+    lib().orc_mesh_project(_p(v), _p(vn), C.c_uint32(v.shape[0]), _p(t), C.c_uint32(t.shape[0]), _p(x), C.c_uint32(N), C.c_uint32(K),
+                           C.c_float(r), C.c_float(dir_vec_wdist), _p(p_sur), _p(sdf), _p(normal), _p(face))
+    return p_sur, sdf, normal, face

@@ -105,3 +105,64 @@ def ulp16(x):
     x = np.abs(np.asarray(x, np.float32))
     e = np.floor(np.log2(np.maximum(x, 2.0 ** -14)))
     return (2.0 ** (e - 10)).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ synthetic meshes
+def bumpy_sphere(n_lat, n_lon, bump=0.1, radius=0.7):
+    """closed-ish lat/lon sphere with a smooth bump pattern: vertices [n,3] f32, faces [m,3] i32, outward vertex normals [n,3] f32"""
+    th = np.linspace(0.05, np.pi - 0.05, n_lat)
+    ph = np.linspace(0, 2 * np.pi, n_lon, endpoint=False)
+    T, P = np.meshgrid(th, ph, indexing="ij")
+    r = radius + bump * np.sin(5 * T) * np.cos(3 * P)
+    v = np.stack([r * np.sin(T) * np.cos(P), r * np.sin(T) * np.sin(P), r * np.cos(T)], -1).reshape(-1, 3).astype(np.float32)
+    i, j = np.meshgrid(np.arange(n_lat - 1), np.arange(n_lon), indexing="ij")
+    a, b = i * n_lon + j, i * n_lon + (j + 1) % n_lon
+    c, d = (i + 1) * n_lon + j, (i + 1) * n_lon + (j + 1) % n_lon
+    f = np.stack([np.stack([a, c, b], -1), np.stack([b, c, d], -1)], 2).reshape(-1, 3).astype(np.int32)
+    return v, f, vertex_normals(v, f)
+
+
+def vertex_normals(v, f):
+    """area-weighted vertex normals (what open3d's compute_vertex_normals gives the reference, tools/map.py:369,394)"""
+    fn = np.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]])
+    vn = np.zeros_like(v)
+    for k in range(3):
+        np.add.at(vn, f[:, k], fn)
+    return (vn / (np.linalg.norm(vn, axis=1, keepdims=True) + 1e-12)).astype(np.float32)
+
+
+def random_rays(rng, n, extent=1.0):
+    o = rng.uniform(-extent, extent, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    return o, (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+
+
+def adversarial_rays(rng, v, f):
+    """rays aimed exactly at vertices, edge midpoints and centroids (ties between the triangles that share them), from inside and from
+    outside; axis-parallel rays from lattice origins (rays that run IN box faces); rays that start on vertices"""
+    tgt = np.concatenate([v, 0.5 * (v[f[:, 0]] + v[f[:, 1]]), (v[f[:, 0]] + v[f[:, 1]] + v[f[:, 2]]) / 3]).astype(np.float32)
+    d = (tgt / np.linalg.norm(tgt, axis=1, keepdims=True)).astype(np.float32)
+    ax = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 4000)] * rng.choice([-1.0, 1.0], (4000, 1)).astype(np.float32)
+    oa = rng.uniform(-1, 1, (4000, 3)).astype(np.float32)
+    oa[:2000] = np.round(oa[:2000] * 4) / 4
+    ov = v[rng.integers(0, len(v), 4000)]
+    dv = rng.normal(size=(4000, 3)).astype(np.float32)
+    o = np.concatenate([np.zeros_like(tgt), 2 * tgt, oa, ov]).astype(np.float32)
+    return o, np.concatenate([d, -d, ax, dv]).astype(np.float32)
+
+
+def build_mesh_host_check():
+    """g++ build of tests/native/mesh_host_check.cpp (the product's tree builder + traversals compiled for the host); returns a CDLL"""
+    import ctypes
+    import subprocess
+    src = os.path.join(ROOT, "tests", "native", "mesh_host_check.cpp")
+    out_dir = os.path.join(ROOT, "tests", "native", "_build")
+    so = os.path.join(out_dir, "libmesh_host_check.so")
+    deps = [src] + [os.path.join(ROOT, "nerf_texture_b200", "csrc", f) for f in ("mesh_bvh.cuh", "mesh_build.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        os.makedirs(out_dir, exist_ok=True)
+        cmd = ["g++", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-std=c++17", "-Wno-unknown-pragmas", "-o", so, src]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("mesh_host_check build failed:\n" + r.stderr[-4000:])
+    return ctypes.CDLL(so)

@@ -29,7 +29,7 @@ import warnings
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STAGE = os.path.join(ROOT, "baseline", "_ref")
 STUBBED = ("turtle", "trimesh", "tensorboardX", "matplotlib", "mcubes", "torch_ema", "plyfile", "pytorch3d", "imageio", "pymesh", "open3d",
-           "cv2", "sklearn", "PIL")
+           "cv2", "sklearn", "PIL", "xatlas")
 
 
 class _Inert:
@@ -118,6 +118,25 @@ def import_reference_network(backend):
     import raymarching
     from nerf.network_ff import NeRFNetwork
     return NeRFNetwork, raymarching
+
+
+def import_reference_map():
+    """the reference's tools/map.py (MeshProjector, map.py:340) over the drop-in `frnn` / `RayTracer` / `tinycudann` / `gridencoder`
+    packages; the mesh libraries it imports at module level (trimesh, xatlas, open3d, pytorch3d) are inert stubs — MeshProjector.project
+    and .knn only use torch, frnn and RayTracer."""
+    import torch  # noqa: F401
+    warnings.filterwarnings("ignore", category=FutureWarning)
+    if not any(isinstance(f, _StubFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _StubFinder())
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import nerf_texture_b200
+    nerf_texture_b200.install()
+    callers = os.path.join(STAGE, "callers")
+    if callers not in sys.path:
+        sys.path.insert(0, callers)
+    import tools.map as ref_map
+    return ref_map
 
 
 def build_model(NeRFNetwork, device, seed=0):

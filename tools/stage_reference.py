@@ -6,8 +6,9 @@
 baseline/_ref/ is git-ignored (nothing of the reference enters the history) but travels to the GPU box with the snapshot,
 like oracle/_ref/ (the reference's CUDA rebuilt for sm_100a).  Two trees are staged:
 
-  baseline/_ref/callers/   nerf/{renderer,network_ff,utils}.py, tools/{encoding,activation,shape_tools,__init__}.py
-                           — the code that CALLS the hot path (renderer.py:338 run_cuda, network_ff.py:55 forward);
+  baseline/_ref/callers/   nerf/{renderer,network_ff,utils}.py, tools/{encoding,activation,shape_tools,map,__init__}.py
+                           — the code that CALLS the hot path (renderer.py:338 run_cuda, network_ff.py:55 forward; map.py:414
+                           MeshProjector.project for the mesh front end);
   baseline/_ref/wrappers/  gridencoder/, ffmlp/, shencoder/, raymarching/ *.py — the reference's own operator wrappers, used only
                            by the reference arm (on top of oracle/_ref/_ref_*.so) in tests/test_gpu_reference_files.py and bench.py.
 
@@ -21,7 +22,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get("NTX_REFERENCE_ROOT", "/root/reference")
 DST = os.path.join(ROOT, "baseline", "_ref")
 
-CALLERS = ["nerf/renderer.py", "nerf/network_ff.py", "nerf/utils.py", "tools/__init__.py", "tools/encoding.py", "tools/activation.py", "tools/shape_tools.py"]
+CALLERS = ["nerf/renderer.py", "nerf/network_ff.py", "nerf/utils.py", "tools/__init__.py", "tools/encoding.py", "tools/activation.py", "tools/shape_tools.py",
+           "tools/map.py"]
 WRAPPERS = ["gridencoder/__init__.py", "gridencoder/grid.py", "gridencoder/grid_clustering.py", "ffmlp/__init__.py", "ffmlp/ffmlp.py",
             "shencoder/__init__.py", "shencoder/sphere_harmonics.py", "raymarching/__init__.py", "raymarching/raymarching.py"]
 
