@@ -149,8 +149,35 @@ struct Hit {
     int slot;     // position in the leaf-ordered triangle array
 };
 
-// Nearest hit with t < kMaxDist.  Ties in t go to the lowest triangle index (what a scan in index order with `t < mint` finds).
-// `slack` widens the pruning interval: the t a triangle test returns carries its own rounding error, the box test must not cut it.
+// ---- the two steps of a nearest-hit traversal -------------------------------------------------------------------------------
+// Inner node: which children can still hold a hit nearer than `best_t` (plus slack: the t a triangle test returns carries its own
+// rounding error, the box test must not cut it).  Returns the number of children to visit (0, 1, 2), nearer one in *c_near.
+NTX_HD int trace_node_step(const Node& nd, const float* ro, const float* inv, float best_t, float slack_abs, int* c_near, int* c_far) {
+    const float limit = best_t + (slack_abs + 4e-6f * best_t);
+    float e0 = box_entry(nd.lo0, nd.hi0, ro, inv, limit, slack_abs);
+    float e1 = box_entry(nd.lo1, nd.hi1, ro, inv, limit, slack_abs);
+    int c0 = nd.c0, c1 = nd.c1;
+    if (e1 < e0) { const float te = e0; e0 = e1; e1 = te; const int tc = c0; c0 = c1; c1 = tc; }
+    *c_near = c0;
+    *c_far = c1;
+    return (e0 < INFINITY) + (e1 < INFINITY);
+}
+
+// Leaf: nearest hit with t < kMaxDist.  Ties in t go to the lowest triangle index (what a scan in index order with `t < mint` finds).
+NTX_HD void trace_leaf_step(const Tri* tris, int link, const float* ro, const float* rd, Hit& best) {
+    const int first = leaf_first(link), count = leaf_count(link);
+    for (int i = 0; i < count; i++) {
+        Tri tr;
+        fetch_tri(tris, first + i, tr);
+        float n[3];
+        const float t = tri_intersect(tr, ro, rd, n);
+        if (t < best.t || (t == best.t && best.face >= 0 && tr.idx < best.face)) {
+            best.t = t; best.face = tr.idx; best.slot = first + i;
+        }
+    }
+}
+
+// One query, start to end (host check; the kernels pull queries dynamically, see *_dynamic below).
 NTX_HD Hit trace_one(const Node* nodes, const Tri* tris, const float* ro, const float* rd, float slack_abs) {
     Hit best{kMaxDist, -1, -1};
     const float inv[3] = {1.0f / rd[0], 1.0f / rd[1], 1.0f / rd[2]};
@@ -161,27 +188,15 @@ NTX_HD Hit trace_one(const Node* nodes, const Tri* tris, const float* ro, const 
         if (cur >= 0) {
             Node nd;
             fetch_node(nodes, cur, nd);
-            const float limit = best.t + (slack_abs + 4e-6f * best.t);
-            float e0 = box_entry(nd.lo0, nd.hi0, ro, inv, limit, slack_abs);
-            float e1 = box_entry(nd.lo1, nd.hi1, ro, inv, limit, slack_abs);
-            int c0 = nd.c0, c1 = nd.c1;
-            if (e1 < e0) { float te = e0; e0 = e1; e1 = te; int tc = c0; c0 = c1; c1 = tc; }
-            if (e0 < INFINITY) {
-                cur = c0;
-                if (e1 < INFINITY && sp < kStackDepth) stack[sp++] = c1;
+            int c_near, c_far;
+            const int n = trace_node_step(nd, ro, inv, best.t, slack_abs, &c_near, &c_far);
+            if (n > 0) {
+                cur = c_near;
+                if (n > 1 && sp < kStackDepth) stack[sp++] = c_far;
                 continue;
             }
         } else {
-            const int first = leaf_first(cur), count = leaf_count(cur);
-            for (int i = 0; i < count; i++) {
-                Tri tr;
-                fetch_tri(tris, first + i, tr);
-                float n[3];
-                const float t = tri_intersect(tr, ro, rd, n);
-                if (t < best.t || (t == best.t && best.face >= 0 && tr.idx < best.face)) {
-                    best.t = t; best.face = tr.idx; best.slot = first + i;
-                }
-            }
+            trace_leaf_step(tris, cur, ro, rd, best);
         }
         if (sp == 0) break;
         cur = stack[--sp];
@@ -202,9 +217,14 @@ NTX_HD void tri_normal(const Tri& tr, float* n) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// K nearest points with squared distance < r2, ascending by (distance, index).  bd/bi hold K entries; returns how many are valid.
+// K nearest points with squared distance < r2, ascending by (distance, index).
 // Distances are ((dx*dx + dy*dy) + dz*dz) of d = q - p; the box bound uses the same operation order on the clamped offsets, and
 // rounding is monotonic, so bound <= distance of every point in the box holds in floating point, not just in the reals.
+//
+// The candidate list is K (compile-time) slots sorted by (distance, index) and only ever indexed by unrolled loop counters, so it
+// lives in registers.  A query for k_want < K neighbours pre-fills the first K - k_want slots with entries that beat everything
+// (distance -1): the real neighbours then occupy the last k_want slots and "the worst entry still of interest" is always slot K-1.
+// Empty slots hold (+inf, INT_MAX), which every real candidate beats.
 NTX_HD float sq_dist3(float dx, float dy, float dz) { return NTX_ADD(NTX_ADD(NTX_MUL(dx, dx), NTX_MUL(dy, dy)), NTX_MUL(dz, dz)); }
 
 NTX_HD float box_sq_dist(const float* lo, const float* hi, const float* q) {
@@ -213,13 +233,59 @@ NTX_HD float box_sq_dist(const float* lo, const float* hi, const float* q) {
     return sq_dist3(d[0], d[1], d[2]);
 }
 
+constexpr int kEmptyIdx = 0x7fffffff;
+
+template <int K>
+NTX_HD void knn_list_init(float* bd, int* bi, int k_want) {
+#pragma unroll
+    for (int s = 0; s < K; s++) {
+        const bool filler = s < K - k_want;
+        bd[s] = filler ? -1.0f : INFINITY;
+        bi[s] = filler ? 0 : kEmptyIdx;
+    }
+}
+
+// s-th neighbour (0-based, s < k_want) after the search: distance / index, or -1 / -1 when fewer were in range.  `s` must be an
+// unrolled loop counter of a loop over 0..K-1 for the list to stay in registers: iterate slots, not neighbours (see the kernels).
+NTX_HD bool knn_slot_valid(int bi_s) { return bi_s != kEmptyIdx; }
+
+NTX_HD int knn_node_step(const Node& nd, const float* q, float r2, float worst, int* c_near, int* c_far) {
+    float e0 = (nd.c0 < 0 && leaf_count(nd.c0) == 0) ? INFINITY : box_sq_dist(nd.lo0, nd.hi0, q);
+    float e1 = (nd.c1 < 0 && leaf_count(nd.c1) == 0) ? INFINITY : box_sq_dist(nd.lo1, nd.hi1, q);
+    int c0 = nd.c0, c1 = nd.c1;
+    if (e1 < e0) { const float te = e0; e0 = e1; e1 = te; const int tc = c0; c0 = c1; c1 = tc; }
+    *c_near = c0;
+    *c_far = c1;
+    // beyond the radius nothing counts; with the list full, nothing beyond its last entry (equal distance: a lower index still does)
+    return (e0 < r2 && e0 <= worst) + (e1 < r2 && e1 <= worst);
+}
+
+template <int K>
+NTX_HD void knn_leaf_step(const Point* pts, int link, const float* q, float r2, float* bd, int* bi) {
+    const int first = leaf_first(link), count = leaf_count(link);
+    for (int i = 0; i < count; i++) {
+        Point p;
+        fetch_point(pts, first + i, p);
+        const float d2 = sq_dist3(NTX_SUB(q[0], p.p[0]), NTX_SUB(q[1], p.p[1]), NTX_SUB(q[2], p.p[2]));
+        if (!(d2 < r2)) continue;
+        if (!(d2 < bd[K - 1] || (d2 == bd[K - 1] && p.idx < bi[K - 1]))) continue;
+        float cd = d2;
+        int ci = p.idx;
+#pragma unroll
+        for (int s = 0; s < K; s++) {   // sorted insertion: the carried entry sinks to its slot, the rest shift down, the last falls out
+            const bool before = cd < bd[s] || (cd == bd[s] && ci < bi[s]);
+            const float td = bd[s];
+            const int ti = bi[s];
+            bd[s] = before ? cd : td; bi[s] = before ? ci : ti;
+            cd = before ? td : cd;    ci = before ? ti : ci;
+        }
+    }
+}
+
+// One query, start to end (host check).  Returns the number of neighbours found (<= k_want); they are in slots K - k_want ...
 template <int K>
 NTX_HD int knn_one(const Node* nodes, const Point* pts, const float* q, float r2, int k_want, float* bd, int* bi) {
-    int found = 0;
-    // (wd, wi) = the k_want-th entry once the list is full: kept in scalars so that bd/bi are only ever indexed by unrolled loop
-    // counters and stay in registers on the device
-    float wd = INFINITY;
-    int wi = 0x7fffffff;
+    knn_list_init<K>(bd, bi, k_want);
     int stack[kStackDepth];
     int sp = 0;
     int cur = 0;
@@ -227,43 +293,138 @@ NTX_HD int knn_one(const Node* nodes, const Point* pts, const float* q, float r2
         if (cur >= 0) {
             Node nd;
             fetch_node(nodes, cur, nd);
-            float e0 = (nd.c0 < 0 && leaf_count(nd.c0) == 0) ? INFINITY : box_sq_dist(nd.lo0, nd.hi0, q);
-            float e1 = (nd.c1 < 0 && leaf_count(nd.c1) == 0) ? INFINITY : box_sq_dist(nd.lo1, nd.hi1, q);
-            int c0 = nd.c0, c1 = nd.c1;
-            if (e1 < e0) { float te = e0; e0 = e1; e1 = te; int tc = c0; c0 = c1; c1 = tc; }
-            // beyond the radius nothing counts; with the list full, nothing beyond its last entry (equal distance: a lower index still does)
-            const bool go0 = e0 < r2 && e0 <= wd, go1 = e1 < r2 && e1 <= wd;
-            if (go0) {
-                cur = c0;
-                if (go1 && sp < kStackDepth) stack[sp++] = c1;
+            int c_near, c_far;
+            const int n = knn_node_step(nd, q, r2, bd[K - 1], &c_near, &c_far);
+            if (n > 0) {
+                cur = c_near;
+                if (n > 1 && sp < kStackDepth) stack[sp++] = c_far;
                 continue;
             }
         } else {
-            const int first = leaf_first(cur), count = leaf_count(cur);
-            for (int i = 0; i < count; i++) {
-                Point p;
-                fetch_point(pts, first + i, p);
-                const float d2 = sq_dist3(NTX_SUB(q[0], p.p[0]), NTX_SUB(q[1], p.p[1]), NTX_SUB(q[2], p.p[2]));
-                if (!(d2 < r2)) continue;
-                if (!(d2 < wd || (d2 == wd && p.idx < wi))) continue;
-                if (found < k_want) found++;
-                float cd = d2;
-                int ci = p.idx;
-#pragma unroll
-                for (int s = 0; s < K; s++) {   // sorted insertion: the carried entry sinks until it finds its slot, the rest shift down
-                    if (s < found) {
-                        const bool before = bi[s] < 0 || cd < bd[s] || (cd == bd[s] && ci < bi[s]);
-                        if (before) { const float td = bd[s]; const int ti = bi[s]; bd[s] = cd; bi[s] = ci; cd = td; ci = ti; }
-                        if (s == k_want - 1) { wd = bd[s]; wi = bi[s]; }
-                    }
-                }
-            }
+            knn_leaf_step<K>(pts, cur, q, r2, bd, bi);
         }
         if (sp == 0) break;   // a popped subtree is re-tested against the current list when its node is fetched
         cur = stack[--sp];
     }
+    int found = 0;
+#pragma unroll
+    for (int s = 0; s < K; s++) found += (s >= K - k_want) && knn_slot_valid(bi[s]);
     return found;
 }
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------------------------------------------
+// Device loops.  A warp owns a chunk of `n_tasks` consecutive queries; its lanes PULL queries one at a time from a shared-memory
+// counter and every lane runs the same flat loop: [take a query if idle] -> [walk inner nodes down to a leaf] -> [scan the leaf] ->
+// [report if the stack is empty].  Queries differ 10x in cost (a sample far from the surface sees many equidistant vertices); with
+// one query per thread a warp waits for its slowest lane (measured: 4.8 of 32 lanes active on average), with pulling a lane that
+// finishes early simply starts the next query.  All 32 lanes must call these together (they vote with __any_sync).
+//   load(task, q...)  fills the query; emit(task, result...) consumes it.
+
+template <class Load, class Emit>
+__device__ __forceinline__ void trace_dynamic(const Node* __restrict__ nodes, const Tri* __restrict__ tris, int n_tasks, float slack_abs, int* ctr,
+                                              Load&& load, Emit&& emit) {
+    bool active = false, exhausted = false;
+    int task = 0, cur = 0, sp = 0;
+    int stack[kStackDepth];
+    float ro[3], rd[3], inv[3];
+    Hit best{kMaxDist, -1, -1};
+    for (;;) {
+        if (!active && !exhausted) {
+            task = atomicAdd(ctr, 1);
+            if (task < n_tasks) {
+                load(task, ro, rd);
+                inv[0] = 1.0f / rd[0]; inv[1] = 1.0f / rd[1]; inv[2] = 1.0f / rd[2];
+                best.t = kMaxDist; best.face = -1; best.slot = -1;
+                cur = 0; sp = 0;
+                active = true;
+            } else {
+                exhausted = true;
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+        if (active) {
+            bool done = false;
+            while (cur >= 0) {
+                Node nd;
+                fetch_node(nodes, cur, nd);
+                int c_near, c_far;
+                const int n = trace_node_step(nd, ro, inv, best.t, slack_abs, &c_near, &c_far);
+                if (n > 0) {
+                    cur = c_near;
+                    if (n > 1 && sp < kStackDepth) stack[sp++] = c_far;
+                } else if (sp > 0) {
+                    cur = stack[--sp];
+                } else {
+                    done = true;
+                    break;
+                }
+            }
+            if (!done) {
+                trace_leaf_step(tris, cur, ro, rd, best);
+                if (sp > 0) cur = stack[--sp];
+                else done = true;
+            }
+            if (done) {
+                emit(task, ro, rd, best);
+                active = false;
+            }
+        }
+    }
+}
+
+template <int K, class Load, class Emit>
+__device__ __forceinline__ void knn_dynamic(const Node* __restrict__ nodes, const Point* __restrict__ pts, int n_tasks, float r2, int k_want, int* ctr,
+                                            Load&& load, Emit&& emit) {
+    bool active = false, exhausted = false;
+    int task = 0, cur = 0, sp = 0;
+    int stack[kStackDepth];
+    float q[3];
+    float bd[K];
+    int bi[K];
+    for (;;) {
+        if (!active && !exhausted) {
+            task = atomicAdd(ctr, 1);
+            if (task < n_tasks) {
+                load(task, q);
+                knn_list_init<K>(bd, bi, k_want);
+                cur = 0; sp = 0;
+                active = true;
+            } else {
+                exhausted = true;
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+        if (active) {
+            bool done = false;
+            while (cur >= 0) {
+                Node nd;
+                fetch_node(nodes, cur, nd);
+                int c_near, c_far;
+                const int n = knn_node_step(nd, q, r2, bd[K - 1], &c_near, &c_far);
+                if (n > 0) {
+                    cur = c_near;
+                    if (n > 1 && sp < kStackDepth) stack[sp++] = c_far;
+                } else if (sp > 0) {
+                    cur = stack[--sp];
+                } else {
+                    done = true;
+                    break;
+                }
+            }
+            if (!done) {
+                knn_leaf_step<K>(pts, cur, q, r2, bd, bi);
+                if (sp > 0) cur = stack[--sp];
+                else done = true;
+            }
+            if (done) {
+                emit(task, q, bd, bi);
+                active = false;
+            }
+        }
+    }
+}
+#endif  // __CUDACC__
 
 }  // namespace mesh
 }  // namespace ntx

@@ -65,11 +65,10 @@ int hostcheck_knn(const float* points, uint32_t n_p, const float* queries, uint3
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t i = 0; i < (int64_t)N; i++) {
         float bd[32]; int bi[32];
-        for (int s = 0; s < 32; s++) { bd[s] = INFINITY; bi[s] = -1; }
         const int found = knn_one<32>(tree.nodes.data(), pts.data(), queries + 3 * i, r2, (int)K, bd, bi);
-        for (uint32_t s = 0; s < K; s++) {
-            dists[(size_t)i * K + s] = (int)s < found ? bd[s] : -1.0f;
-            idxs[(size_t)i * K + s] = (int)s < found ? bi[s] : -1;
+        for (uint32_t s = 0; s < K; s++) {   // the neighbours sit in the LAST K slots of the list (mesh_bvh.cuh)
+            dists[(size_t)i * K + s] = (int)s < found ? bd[32 - K + s] : -1.0f;
+            idxs[(size_t)i * K + s] = (int)s < found ? bi[32 - K + s] : -1;
         }
     }
     return tree.depth;
