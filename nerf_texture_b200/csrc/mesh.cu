@@ -4,8 +4,9 @@
 //
 // Trees in the 64-byte two-box node format of mesh_bvh.cuh, read through the read-only path (the trees of the reference's meshes —
 // 10^4..10^6 triangles, <= 100 MB — live in the 126 MB L2 after the first wave; one 4 x LDG.128 node fetch decides both children).
-// Every warp owns a chunk of consecutive queries and its lanes pull them one by one (mesh_bvh.cuh, *_dynamic): these are
-// pointer chases whose length varies 10x from query to query, so the unit of scheduling is the query, not the thread.
+// Ray casts run one thread per ray (neighbouring samples cast neighbouring rays: the warp stays together); the neighbour search
+// for K <= 8 runs 8 lanes per query on an 8-wide tree with the groups of a warp pulling queries from its chunk (mesh_bvh.cuh,
+// knn8_dynamic) — one thread per query left 4.8 of 32 lanes busy there.
 #include "common.cuh"
 #include "mesh_build.h"
 
@@ -27,12 +28,14 @@ struct MeshHandle {
     Tri* tris;
     Node* pt_nodes;
     Point* pts;
+    Node8* pt_nodes8;     // the same vertices as an 8-wide tree (K <= 8: 8 lanes per query)
+    uint32_t pt_nodes8_n, pt_depth8;
     float* vertices;      // [n_vertices, 3] in the caller's order (the fused projection gathers neighbours by index)
 };
 
 static void free_handle(MeshHandle* h) {
     if (!h) return;
-    cudaFree(h->tri_nodes); cudaFree(h->tris); cudaFree(h->pt_nodes); cudaFree(h->pts); cudaFree(h->vertices);
+    cudaFree(h->tri_nodes); cudaFree(h->tris); cudaFree(h->pt_nodes); cudaFree(h->pts); cudaFree(h->pt_nodes8); cudaFree(h->vertices);
     h->magic = 0;
     delete h;
 }
@@ -50,106 +53,81 @@ __device__ __forceinline__ void load3(const float* p, uint32_t i, float* v) {
     v[0] = p[3 * (size_t)i]; v[1] = p[3 * (size_t)i + 1]; v[2] = p[3 * (size_t)i + 2];
 }
 
-constexpr int kWarps = 2;                 // warps per block; each warp owns one chunk of `chunk` consecutive queries
-constexpr int kThreads = kWarps * 32;
-constexpr int kMaxProjectChunk = 128;     // 28 B of shared memory per sample of a projection chunk
+// ---- one thread per query: ray casts (coherent by construction: neighbouring samples cast neighbouring rays), and the neighbour
+// search for K > 8 -------------------------------------------------------------------------------------------------------------
 
-// queries per warp: enough warps to fill the GPU (24 per SM) first, then up to 8 queries per lane so that pulling can even out their cost
-static uint32_t chunk_for(uint32_t N, uint32_t max_chunk) {
-    const uint64_t target_warps = (uint64_t)device_sm_count() * 24;
-    const uint32_t per_lane = (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(2, N / (32 * target_warps)));
-    return std::min(32 * per_lane, max_chunk);
-}
-
-// bvh.cu:695-721 raytrace_kernel.  positions may alias rays_o and normals rays_d (raytracer.py:52-54 `inplace`): a lane reads its
-// ray before it writes that row, and no other lane touches the row.
-__global__ void __launch_bounds__(kThreads) mesh_trace_kernel(uint32_t N, uint32_t chunk, const float* rays_o, const float* rays_d, float* positions,
-                                                              float* normals, float* depth, long long* face_idx, const Node* __restrict__ nodes,
-                                                              const Tri* __restrict__ tris, float slack) {
-    __shared__ int ctr[kWarps];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t base64 = ((uint64_t)blockIdx.x * kWarps + warp) * chunk;
-    if (base64 >= N) return;   // warp-uniform
-    const uint32_t base = (uint32_t)base64;
-    const int n = (int)min(chunk, N - base);
-    if (lane == 0) ctr[warp] = 0;
-    __syncwarp();
-    trace_dynamic(
-        nodes, tris, n, slack, &ctr[warp],
-        [&](int task, float* ro, float* rd) {
-            load3(rays_o, base + task, ro);
-            load3(rays_d, base + task, rd);
-        },
-        [&](int task, const float* ro, const float* rd, const Hit& h) {
-            const size_t i = base + task;
-            depth[i] = h.t;
-            for (int k = 0; k < 3; k++) positions[3 * i + k] = NTX_ADD(ro[k], NTX_MUL(h.t, rd[k]));
-            float nrm[3] = {0.0f, 0.0f, 0.0f};
-            if (h.face >= 0) {
-                Tri tr;
-                fetch_tri(tris, h.slot, tr);
-                tri_normal(tr, nrm);
-                face_idx[i] = h.face;   // a miss leaves the caller's value (the reference pre-fills -1, raytracer.py:37)
-            }
-            for (int k = 0; k < 3; k++) normals[3 * i + k] = nrm[k];
-        });
+// bvh.cu:695-721 raytrace_kernel.  positions may alias rays_o and normals rays_d (raytracer.py:52-54 `inplace`): a thread reads its
+// ray before it writes anything.
+__global__ void __launch_bounds__(128) mesh_trace_kernel(uint32_t N, const float* rays_o, const float* rays_d, float* positions, float* normals,
+                                                         float* depth, long long* face_idx, const Node* __restrict__ nodes,
+                                                         const Tri* __restrict__ tris, float slack) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float ro[3], rd[3];
+    load3(rays_o, i, ro);
+    load3(rays_d, i, rd);
+    const Hit h = trace_one(nodes, tris, ro, rd, slack);
+    depth[i] = h.t;
+    for (int k = 0; k < 3; k++) positions[3 * (size_t)i + k] = NTX_ADD(ro[k], NTX_MUL(h.t, rd[k]));
+    float n[3] = {0.0f, 0.0f, 0.0f};
+    if (h.face >= 0) {
+        Tri tr;
+        fetch_tri(tris, h.slot, tr);
+        tri_normal(tr, n);
+        face_idx[i] = h.face;   // a miss leaves the caller's value (the reference pre-fills -1, raytracer.py:37)
+    }
+    for (int k = 0; k < 3; k++) normals[3 * (size_t)i + k] = n[k];
 }
 
 template <int K>
-__global__ void __launch_bounds__(kThreads) mesh_knn_kernel(uint32_t N, uint32_t chunk, const float* queries, float r2, int k_want,
-                                                            const Node* __restrict__ nodes, const Point* __restrict__ pts, float* dists, long long* idxs) {
-    __shared__ int ctr[kWarps];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t base64 = ((uint64_t)blockIdx.x * kWarps + warp) * chunk;
-    if (base64 >= N) return;
-    const uint32_t base = (uint32_t)base64;
-    const int n = (int)min(chunk, N - base);
-    if (lane == 0) ctr[warp] = 0;
-    __syncwarp();
-    knn_dynamic<K>(
-        nodes, pts, n, r2, k_want, &ctr[warp], [&](int task, float* q) { load3(queries, base + task, q); },
-        [&](int task, const float*, const float* bd, const int* bi) {
-            const size_t row = (size_t)(base + task) * k_want;
+__global__ void __launch_bounds__(128) mesh_knn_kernel(uint32_t N, const float* queries, float r2, int k_want, const Node* __restrict__ nodes,
+                                                       const Point* __restrict__ pts, float* dists, long long* idxs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float q[3];
+    load3(queries, i, q);
+    float bd[K];
+    int bi[K];
+    knn_one<K>(nodes, pts, q, r2, k_want, bd, bi);
+    const size_t row = (size_t)i * k_want;
 #pragma unroll
-            for (int s = 0; s < K; s++) {
-                if (s >= K - k_want) {
-                    const bool ok = knn_slot_valid(bi[s]);
-                    dists[row + s - (K - k_want)] = ok ? bd[s] : -1.0f;
-                    idxs[row + s - (K - k_want)] = ok ? bi[s] : -1;
-                }
-            }
-        });
+    for (int s = 0; s < K; s++) {
+        if (s >= K - k_want) {
+            const bool ok = knn_slot_valid(bi[s]);
+            dists[row + s - (K - k_want)] = ok ? bd[s] : -1.0f;
+            idxs[row + s - (K - k_want)] = ok ? bi[s] : -1;
+        }
+    }
 }
 
 __device__ __forceinline__ float norm3(const float* v) { return sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
 
-// tools/map.py:454-500 from a finished neighbour list (knn with use_dir_vec=True, weighting='Shepard').  The weighted-normal
-// arithmetic is plain fp32 (the reference's is a chain of ~30 torch kernels over [N,K,3] temporaries whose reduction order is not
-// specified — parity is to tolerance there, see the tests).
-template <int K>
-__device__ __forceinline__ void coarse_normal(const float* x, const float* bd, const int* bi, int k_want, float dir_vec_wdist,
-                                              const float* __restrict__ vertices, const float* __restrict__ vertex_normals, uint32_t n_vertices, float* n) {
-    float mean_dir[3] = {0, 0, 0}, ntest[3] = {0, 0, 0}, acc[3] = {0, 0, 0}, wsum = 0.0f;
-#pragma unroll
-    for (int s = 0; s < K; s++) {
-        if (s >= K - k_want) {
-            // fewer than K vertices in the radius: frnn pads with -1, which torch's indexing wraps to the last vertex, sqrt(-1) = NaN (:458)
-            const bool ok = knn_slot_valid(bi[s]);
-            const uint32_t j = ok ? (uint32_t)bi[s] : n_vertices - 1;
-            const float dis = ok ? sqrtf(bd[s]) : NAN;
-            float vn[3], dvo[3];
-            for (int c = 0; c < 3; c++) { vn[c] = __ldg(vertex_normals + 3 * (size_t)j + c); dvo[c] = x[c] - __ldg(vertices + 3 * (size_t)j + c); }
-            const float len = norm3(dvo) + 1e-5f;                 // :461
-            const float w = 1.0f / (dis + 1e-7f);                 // :474 and :487 (Shepard): the same weight twice
-            const float nl = norm3(vn) + 1e-5f;                   // :497
-            for (int c = 0; c < 3; c++) {
-                mean_dir[c] += w * (dvo[c] / len);                // :476
-                ntest[c] += vn[c];                                // :477
-                acc[c] += (vn[c] / nl) * w;                       // :498 before the division by the weight sum
-            }
-            wsum += w;
-        }
+// tools/map.py:454-500 (knn with use_dir_vec=True, weighting='Shepard'): the terms one neighbour contributes.  The arithmetic is plain
+// fp32 (the reference's is a chain of ~30 torch kernels over [N,K,3] temporaries whose reduction order is not specified — parity is to
+// tolerance there, see the tests).  sums = {mean_dir[3], normal_test[3], weighted normals[3], weight sum}
+__device__ __forceinline__ void neighbour_terms(const float* x, bool ok, float d2, int idx, const float* __restrict__ vertices,
+                                                const float* __restrict__ vertex_normals, uint32_t n_vertices, float* sums) {
+    // fewer than K vertices in the radius: frnn pads with -1, which torch's indexing wraps to the last vertex, sqrt(-1) = NaN (:458)
+    const uint32_t j = ok ? (uint32_t)idx : n_vertices - 1;
+    const float dis = ok ? sqrtf(d2) : NAN;
+    float vn[3], dvo[3];
+    for (int c = 0; c < 3; c++) { vn[c] = __ldg(vertex_normals + 3 * (size_t)j + c); dvo[c] = x[c] - __ldg(vertices + 3 * (size_t)j + c); }
+    const float len = norm3(dvo) + 1e-5f;                 // :461
+    const float w = 1.0f / (dis + 1e-7f);                 // :474 and :487 (Shepard): the same weight twice
+    const float nl = norm3(vn) + 1e-5f;                   // :497
+    for (int c = 0; c < 3; c++) {
+        sums[c] += w * (dvo[c] / len);                    // :476
+        sums[3 + c] += vn[c];                             // :477
+        sums[6 + c] += (vn[c] / nl) * w;                  // :498 before the division by the weight sum
     }
+    sums[9] += w;
+}
+
+__device__ __forceinline__ void finish_normal(float* sums, int k_want, float dir_vec_wdist, float* n) {
+    float* mean_dir = sums;
+    float* ntest = sums + 3;
+    float* acc = sums + 6;
+    float wsum = sums[9];
     for (int c = 0; c < 3; c++) ntest[c] /= (float)k_want;
     if (mean_dir[0] * ntest[0] + mean_dir[1] * ntest[1] + mean_dir[2] * ntest[2] < 0.0f)
         for (int c = 0; c < 3; c++) mean_dir[c] = -mean_dir[c];  // :478
@@ -166,61 +144,127 @@ __device__ __forceinline__ void coarse_normal(const float* x, const float* bd, c
     for (int c = 0; c < 3; c++) n[c] = acc[c] / len;
 }
 
-// tools/map.py:414-433 for one chunk of samples per warp, three phases over the same chunk:
-//   A  neighbour search (lanes pull samples), coarse normal straight from the register list -> shared memory
-//   B  2 x chunk ray casts along +-normal (lanes pull (sample, side) pairs) -> depth / face per side in shared memory
-//   C  select the nearer side (:421-425), coalesced stores
+// tools/map.py:421-425 after the two casts of :419-420
+__device__ __forceinline__ void project_outputs(size_t i, const float* x, const float* n, const Hit& h1, const Hit& h2, float* p_sur, float* sdf,
+                                                float* normal_out, long long* face_idx) {
+    const bool cond = h1.t < h2.t;                                 // :421
+    const float t = cond ? h1.t : h2.t;
+    for (int c = 0; c < 3; c++) {
+        p_sur[3 * i + c] = NTX_ADD(x[c], NTX_MUL(t, cond ? n[c] : -n[c]));   // :422
+        normal_out[3 * i + c] = n[c];
+    }
+    sdf[i] = cond ? -h1.t : h2.t;                                  // :423
+    face_idx[i] = cond ? h1.face : h2.face;                        // :425
+}
+
+// MeshProjector.project, one thread per sample (K > 8; K <= 8 takes mesh_project8_kernel)
 template <int K>
-__global__ void __launch_bounds__(kThreads) mesh_project_kernel(uint32_t N, uint32_t chunk, const float* xyz, int k_want, float r2, float dir_vec_wdist,
-                                                                const float* __restrict__ vertices, const float* __restrict__ vertex_normals,
-                                                                uint32_t n_vertices, const Node* __restrict__ pt_nodes, const Point* __restrict__ pts,
-                                                                const Node* __restrict__ tri_nodes, const Tri* __restrict__ tris, float slack,
-                                                                float* p_sur, float* sdf, float* normal_out, long long* face_idx) {
-    __shared__ int ctr[kWarps];
-    __shared__ float s_normal[kWarps][kMaxProjectChunk][3];
-    __shared__ float s_depth[kWarps][kMaxProjectChunk][2];
-    __shared__ int s_face[kWarps][kMaxProjectChunk][2];
+__global__ void __launch_bounds__(128) mesh_project_kernel(uint32_t N, const float* xyz, int k_want, float r2, float dir_vec_wdist,
+                                                           const float* __restrict__ vertices, const float* __restrict__ vertex_normals,
+                                                           uint32_t n_vertices, const Node* __restrict__ pt_nodes, const Point* __restrict__ pts,
+                                                           const Node* __restrict__ tri_nodes, const Tri* __restrict__ tris, float slack,
+                                                           float* p_sur, float* sdf, float* normal_out, long long* face_idx) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float x[3];
+    load3(xyz, i, x);
+    float bd[K];
+    int bi[K];
+    knn_one<K>(pt_nodes, pts, x, r2, k_want, bd, bi);
+    float sums[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int s = 0; s < K; s++)
+        if (s >= K - k_want) neighbour_terms(x, knn_slot_valid(bi[s]), bd[s], bi[s], vertices, vertex_normals, n_vertices, sums);
+    float n[3], nn[3];
+    finish_normal(sums, k_want, dir_vec_wdist, n);
+    for (int c = 0; c < 3; c++) nn[c] = -n[c];
+    const Hit h1 = trace_one(tri_nodes, tris, x, n, slack);        // :419 inner
+    const Hit h2 = trace_one(tri_nodes, tris, x, nn, slack);       // :420 outer
+    project_outputs(i, x, n, h1, h2, p_sur, sdf, normal_out, face_idx);
+}
+
+// ---- 8 lanes per query: the neighbour search for K <= 8 (mesh_bvh.cuh, knn8_dynamic) ----------------------------------------------
+constexpr int kWarps8 = 2;                // warps per block; each warp owns one chunk of consecutive queries, its 4 groups pull from it
+constexpr int kThreads8 = kWarps8 * 32;
+constexpr int kMaxChunk8 = 256;
+
+// queries per warp: enough warps to fill the GPU (24 per SM) first, then up to 64 queries per group so that pulling evens out their cost
+static uint32_t chunk8_for(uint32_t N) {
+    const uint64_t target_warps = (uint64_t)device_sm_count() * 24;
+    const uint64_t per_warp = std::min<uint64_t>(kMaxChunk8, std::max<uint64_t>(32, N / target_warps));
+    return (uint32_t)(per_warp / 32 * 32);
+}
+
+__global__ void __launch_bounds__(kThreads8) mesh_knn8_kernel(uint32_t N, uint32_t chunk, const float* queries, float r2, int k_want,
+                                                              const Node8* __restrict__ nodes, float* dists, long long* idxs) {
+    __shared__ int ctr[kWarps8];
+    __shared__ uint2 stacks[kWarps8 * 4][kStack8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t base64 = ((uint64_t)blockIdx.x * kWarps + warp) * chunk;
-    if (base64 >= N) return;
+    const uint64_t base64 = ((uint64_t)blockIdx.x * kWarps8 + warp) * chunk;
+    if (base64 >= N) return;   // warp-uniform
     const uint32_t base = (uint32_t)base64;
     const int n = (int)min(chunk, N - base);
     if (lane == 0) ctr[warp] = 0;
     __syncwarp();
-    knn_dynamic<K>(
-        pt_nodes, pts, n, r2, k_want, &ctr[warp], [&](int task, float* q) { load3(xyz, base + task, q); },
-        [&](int task, const float* q, const float* bd, const int* bi) {
-            float nn[3];
-            coarse_normal<K>(q, bd, bi, k_want, dir_vec_wdist, vertices, vertex_normals, n_vertices, nn);
-            for (int c = 0; c < 3; c++) s_normal[warp][task][c] = nn[c];
+    knn8_dynamic(
+        nodes, n, r2, k_want, &ctr[warp], stacks[warp * 4 + (lane >> 3)], [&](int task, float* q) { load3(queries, base + task, q); },
+        [&](int task, const float*, float bd, int bi) {
+            const int j = (lane & 7) - (8 - k_want);   // lane s holds the s-th slot; the neighbours are the last k_want
+            if (j >= 0) {
+                const bool ok = knn_slot_valid(bi);
+                const size_t at = (size_t)(base + task) * k_want + j;
+                dists[at] = ok ? bd : -1.0f;
+                idxs[at] = ok ? bi : -1;
+            }
         });
-    __syncwarp();
+}
+
+// tools/map.py:414-433 for one chunk of samples per warp:
+//   A  neighbour search, 8 lanes per sample; each lane forms the terms of ITS neighbour, a 3-step butterfly sums them, lane 0 of the
+//      group finishes the coarse normal -> shared memory
+//   B  one thread per sample: the two casts along +-normal (neighbouring lanes = neighbouring samples: coherent), select, store
+__global__ void __launch_bounds__(kThreads8) mesh_project8_kernel(uint32_t N, uint32_t chunk, const float* xyz, int k_want, float r2, float dir_vec_wdist,
+                                                                  const float* __restrict__ vertices, const float* __restrict__ vertex_normals,
+                                                                  uint32_t n_vertices, const Node8* __restrict__ pt_nodes,
+                                                                  const Node* __restrict__ tri_nodes, const Tri* __restrict__ tris, float slack,
+                                                                  float* p_sur, float* sdf, float* normal_out, long long* face_idx) {
+    __shared__ int ctr[kWarps8];
+    __shared__ uint2 stacks[kWarps8 * 4][kStack8];
+    __shared__ float s_normal[kWarps8][kMaxChunk8][3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t base64 = ((uint64_t)blockIdx.x * kWarps8 + warp) * chunk;
+    if (base64 >= N) return;
+    const uint32_t base = (uint32_t)base64;
+    const int n = (int)min(chunk, N - base);
+    const unsigned gmask = 0xffu << (lane & ~7);
     if (lane == 0) ctr[warp] = 0;
     __syncwarp();
-    trace_dynamic(
-        tri_nodes, tris, 2 * n, slack, &ctr[warp],
-        [&](int task, float* ro, float* rd) {
-            load3(xyz, base + (task >> 1), ro);
-            const float sgn = (task & 1) ? -1.0f : 1.0f;           // side 0: along the normal (:419 inner), side 1: against it (:420 outer)
-            for (int c = 0; c < 3; c++) rd[c] = sgn * s_normal[warp][task >> 1][c];
-        },
-        [&](int task, const float*, const float*, const Hit& h) {
-            s_depth[warp][task >> 1][task & 1] = h.t;
-            s_face[warp][task >> 1][task & 1] = h.face;
+    knn8_dynamic(
+        pt_nodes, n, r2, k_want, &ctr[warp], stacks[warp * 4 + (lane >> 3)], [&](int task, float* q) { load3(xyz, base + task, q); },
+        [&](int task, const float* q, float bd, int bi) {
+            float sums[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            if ((lane & 7) >= 8 - k_want) neighbour_terms(q, knn_slot_valid(bi), bd, bi, vertices, vertex_normals, n_vertices, sums);
+#pragma unroll
+            for (int c = 0; c < 10; c++) {
+                sums[c] += __shfl_xor_sync(gmask, sums[c], 4);
+                sums[c] += __shfl_xor_sync(gmask, sums[c], 2);
+                sums[c] += __shfl_xor_sync(gmask, sums[c], 1);
+            }
+            if ((lane & 7) == 0) {
+                float nn[3];
+                finish_normal(sums, k_want, dir_vec_wdist, nn);
+                for (int c = 0; c < 3; c++) s_normal[warp][task][c] = nn[c];
+            }
         });
     __syncwarp();
     for (int j = lane; j < n; j += 32) {
         const size_t i = base + j;
-        const float d1 = s_depth[warp][j][0], d2 = s_depth[warp][j][1];
-        const bool cond = d1 < d2;                                 // :421
-        const float t = cond ? d1 : d2;
-        for (int c = 0; c < 3; c++) {
-            const float nc = s_normal[warp][j][c];
-            p_sur[3 * i + c] = NTX_ADD(xyz[3 * i + c], NTX_MUL(t, cond ? nc : -nc));   // :422
-            normal_out[3 * i + c] = nc;
-        }
-        sdf[i] = cond ? -d1 : d2;                                  // :423
-        face_idx[i] = cond ? s_face[warp][j][0] : s_face[warp][j][1];   // :425
+        float x[3], nrm[3], neg[3];
+        load3(xyz, (uint32_t)i, x);
+        for (int c = 0; c < 3; c++) { nrm[c] = s_normal[warp][j][c]; neg[c] = -nrm[c]; }
+        const Hit h1 = trace_one(tri_nodes, tris, x, nrm, slack);   // :419 inner
+        const Hit h2 = trace_one(tri_nodes, tris, x, neg, slack);   // :420 outer
+        project_outputs(i, x, nrm, h1, h2, p_sur, sdf, normal_out, face_idx);
     }
 }
 
@@ -253,6 +297,10 @@ int ntx_mesh_create(const float* vertices, uint32_t n_vertices, const int32_t* t
     NTX_REQUIRE(build_triangle_tree(vertices, n_vertices, triangles, n_triangles, tri_tree, tris), NTX_ERR_INVALID_ARGUMENT,
                 "ntx_mesh_create: non-finite vertex or triangle index out of range");
     NTX_REQUIRE(build_point_tree(vertices, n_vertices, pt_tree, pts), NTX_ERR_INVALID_ARGUMENT, "ntx_mesh_create: non-finite vertex");
+    std::vector<Node8> nodes8;
+    int depth8 = 0;
+    NTX_REQUIRE(build_point_tree8(vertices, n_vertices, nodes8, depth8), NTX_ERR_INVALID_ARGUMENT, "ntx_mesh_create: non-finite vertex");
+    NTX_REQUIRE(7 * depth8 + 1 <= kStack8, NTX_ERR_UNSUPPORTED, "ntx_mesh_create: 8-wide tree deeper than its stack");
     NTX_REQUIRE(tri_tree.depth < kStackDepth && pt_tree.depth < kStackDepth, NTX_ERR_UNSUPPORTED, "ntx_mesh_create: tree deeper than %d", kStackDepth);
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (uint32_t i = 0; i < n_vertices; i++)
@@ -265,9 +313,11 @@ int ntx_mesh_create(const float* vertices, uint32_t n_vertices, const int32_t* t
     h->n_vertices = n_vertices; h->n_triangles = n_triangles;
     h->tri_nodes_n = (uint32_t)tri_tree.nodes.size(); h->pt_nodes_n = (uint32_t)pt_tree.nodes.size();
     h->tri_depth = tri_tree.depth; h->pt_depth = pt_tree.depth;
+    h->pt_nodes8_n = (uint32_t)nodes8.size(); h->pt_depth8 = (uint32_t)depth8;
     h->slack = 1e-5f * std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
     std::vector<float> verts(vertices, vertices + 3 * (size_t)n_vertices);
     const bool ok = upload(&h->tri_nodes, tri_tree.nodes) && upload(&h->tris, tris) && upload(&h->pt_nodes, pt_tree.nodes) && upload(&h->pts, pts) &&
+                    upload(&h->pt_nodes8, nodes8) &&
                     upload(&h->vertices, verts);
     if (!ok) {
         set_error("ntx_mesh_create: %s", cudaGetErrorString(cudaGetLastError()));
@@ -303,9 +353,8 @@ int ntx_mesh_trace(const void* mesh, const float* rays_o, const float* rays_d, f
     if (!h) return NTX_ERR_INVALID_ARGUMENT;
     if (N == 0) return NTX_OK;
     NTX_REQUIRE(rays_o && rays_d && positions && normals && depth && face_idx, NTX_ERR_INVALID_ARGUMENT, "ntx_mesh_trace: null pointer");
-    const uint32_t chunk = chunk_for(N, 256);
-    mesh_trace_kernel<<<ceil_div(N, chunk * kWarps), kThreads, 0, (cudaStream_t)stream>>>(N, chunk, rays_o, rays_d, positions, normals, depth,
-                                                                                         (long long*)face_idx, h->tri_nodes, h->tris, h->slack);
+    mesh_trace_kernel<<<ceil_div(N, 128u), 128, 0, (cudaStream_t)stream>>>(N, rays_o, rays_d, positions, normals, depth, (long long*)face_idx,
+                                                                          h->tri_nodes, h->tris, h->slack);
     return check_launch("ntx_mesh_trace");
 }
 
@@ -316,13 +365,19 @@ int ntx_mesh_knn(const void* mesh, const float* queries, uint32_t N, uint32_t K,
     NTX_REQUIRE(r > 0.0f, NTX_ERR_INVALID_ARGUMENT, "ntx_mesh_knn: r must be positive");
     if (N == 0) return NTX_OK;
     NTX_REQUIRE(queries && dists && idxs, NTX_ERR_INVALID_ARGUMENT, "ntx_mesh_knn: null pointer");
-    const uint32_t chunk = chunk_for(N, 256);
-    const dim3 grid(ceil_div(N, chunk * kWarps));
     cudaStream_t st = (cudaStream_t)stream;
     const float r2 = r * r;
-    if (K <= 8) mesh_knn_kernel<8><<<grid, kThreads, 0, st>>>(N, chunk, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
-    else if (K <= 16) mesh_knn_kernel<16><<<grid, kThreads, 0, st>>>(N, chunk, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
-    else mesh_knn_kernel<32><<<grid, kThreads, 0, st>>>(N, chunk, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
+    const dim3 grid(ceil_div(N, 128u));
+    if (K <= 8 && !tunables().mesh_thread_knn) {
+        const uint32_t chunk = chunk8_for(N);
+        mesh_knn8_kernel<<<ceil_div(N, chunk * kWarps8), kThreads8, 0, st>>>(N, chunk, queries, r2, (int)K, h->pt_nodes8, dists, (long long*)idxs);
+    } else if (K <= 8) {
+        mesh_knn_kernel<8><<<grid, 128, 0, st>>>(N, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
+    } else if (K <= 16) {
+        mesh_knn_kernel<16><<<grid, 128, 0, st>>>(N, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
+    } else {
+        mesh_knn_kernel<32><<<grid, 128, 0, st>>>(N, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
+    }
     return check_launch("ntx_mesh_knn");
 }
 
@@ -335,16 +390,21 @@ int ntx_mesh_project(const void* mesh, const float* vertex_normals, const float*
     NTX_REQUIRE(h->n_triangles > 0, NTX_ERR_INVALID_ARGUMENT, "ntx_mesh_project: the mesh has no triangles");
     if (N == 0) return NTX_OK;
     NTX_REQUIRE(vertex_normals && xyz && p_sur && sdf && normal && face_idx, NTX_ERR_INVALID_ARGUMENT, "ntx_mesh_project: null pointer");
-    const uint32_t chunk = chunk_for(N, kMaxProjectChunk);
-    const dim3 grid(ceil_div(N, chunk * kWarps));
     cudaStream_t st = (cudaStream_t)stream;
     const float r2 = r * r;
-    if (K <= 8)
-        mesh_project_kernel<8><<<grid, kThreads, 0, st>>>(N, chunk, xyz, (int)K, r2, dir_vec_wdist, h->vertices, vertex_normals, h->n_vertices, h->pt_nodes, h->pts,
+    const dim3 grid(ceil_div(N, 128u));
+    if (K <= 8 && !tunables().mesh_thread_knn) {
+        const uint32_t chunk = chunk8_for(N);
+        mesh_project8_kernel<<<ceil_div(N, chunk * kWarps8), kThreads8, 0, st>>>(N, chunk, xyz, (int)K, r2, dir_vec_wdist, h->vertices, vertex_normals,
+                                                                                 h->n_vertices, h->pt_nodes8, h->tri_nodes, h->tris, h->slack, p_sur, sdf,
+                                                                                 normal, (long long*)face_idx);
+    } else if (K <= 8) {
+        mesh_project_kernel<8><<<grid, 128, 0, st>>>(N, xyz, (int)K, r2, dir_vec_wdist, h->vertices, vertex_normals, h->n_vertices, h->pt_nodes, h->pts,
                                                      h->tri_nodes, h->tris, h->slack, p_sur, sdf, normal, (long long*)face_idx);
-    else
-        mesh_project_kernel<16><<<grid, kThreads, 0, st>>>(N, chunk, xyz, (int)K, r2, dir_vec_wdist, h->vertices, vertex_normals, h->n_vertices, h->pt_nodes, h->pts,
+    } else {
+        mesh_project_kernel<16><<<grid, 128, 0, st>>>(N, xyz, (int)K, r2, dir_vec_wdist, h->vertices, vertex_normals, h->n_vertices, h->pt_nodes, h->pts,
                                                       h->tri_nodes, h->tris, h->slack, p_sur, sdf, normal, (long long*)face_idx);
+    }
     return check_launch("ntx_mesh_project");
 }
 
