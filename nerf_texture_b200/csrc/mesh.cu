@@ -4,9 +4,10 @@
 //
 // Trees in the 64-byte two-box node format of mesh_bvh.cuh, read through the read-only path (the trees of the reference's meshes —
 // 10^4..10^6 triangles, <= 100 MB — live in the 126 MB L2 after the first wave; one 4 x LDG.128 node fetch decides both children).
-// Ray casts run one thread per ray (neighbouring samples cast neighbouring rays: the warp stays together); the neighbour search
-// for K <= 8 runs 8 lanes per query on an 8-wide tree with the groups of a warp pulling queries from its chunk (mesh_bvh.cuh,
-// knn8_dynamic) — one thread per query left 4.8 of 32 lanes busy there.
+// One thread per query: neighbouring samples of a camera ray walk nearly the same nodes, and the per-thread state (a 64-entry
+// stack in local memory, the K-entry neighbour list in registers) is small.  Two other mappings were built, verified bit-exact and
+// measured slower on B200 ("Tried and lost"; profiles/r02_mesh_ab_*): lanes pulling queries from a per-warp chunk, and
+// 8 lanes per query on an 8-wide tree.
 #include "common.cuh"
 #include "mesh_build.h"
 
@@ -28,14 +29,12 @@ struct MeshHandle {
     Tri* tris;
     Node* pt_nodes;
     Point* pts;
-    Node8* pt_nodes8;     // the same vertices as an 8-wide tree (K <= 8: 8 lanes per query)
-    uint32_t pt_nodes8_n, pt_depth8;
     float* vertices;      // [n_vertices, 3] in the caller's order (the fused projection gathers neighbours by index)
 };
 
 static void free_handle(MeshHandle* h) {
     if (!h) return;
-    cudaFree(h->tri_nodes); cudaFree(h->tris); cudaFree(h->pt_nodes); cudaFree(h->pts); cudaFree(h->pt_nodes8); cudaFree(h->vertices);
+    cudaFree(h->tri_nodes); cudaFree(h->tris); cudaFree(h->pt_nodes); cudaFree(h->pts); cudaFree(h->vertices);
     h->magic = 0;
     delete h;
 }
@@ -52,9 +51,6 @@ static bool upload(T** dst, const std::vector<T>& src) {
 __device__ __forceinline__ void load3(const float* p, uint32_t i, float* v) {
     v[0] = p[3 * (size_t)i]; v[1] = p[3 * (size_t)i + 1]; v[2] = p[3 * (size_t)i + 2];
 }
-
-// ---- one thread per query: ray casts (coherent by construction: neighbouring samples cast neighbouring rays), and the neighbour
-// search for K > 8 -------------------------------------------------------------------------------------------------------------
 
 // bvh.cu:695-721 raytrace_kernel.  positions may alias rays_o and normals rays_d (raytracer.py:52-54 `inplace`): a thread reads its
 // ray before it writes anything.
@@ -157,7 +153,7 @@ __device__ __forceinline__ void project_outputs(size_t i, const float* x, const 
     face_idx[i] = cond ? h1.face : h2.face;                        // :425
 }
 
-// MeshProjector.project, one thread per sample (K > 8; K <= 8 takes mesh_project8_kernel)
+// MeshProjector.project, one thread per sample: the neighbour list never leaves the registers, both casts run back to back
 template <int K>
 __global__ void __launch_bounds__(128) mesh_project_kernel(uint32_t N, const float* xyz, int k_want, float r2, float dir_vec_wdist,
                                                            const float* __restrict__ vertices, const float* __restrict__ vertex_normals,
@@ -181,91 +177,6 @@ __global__ void __launch_bounds__(128) mesh_project_kernel(uint32_t N, const flo
     const Hit h1 = trace_one(tri_nodes, tris, x, n, slack);        // :419 inner
     const Hit h2 = trace_one(tri_nodes, tris, x, nn, slack);       // :420 outer
     project_outputs(i, x, n, h1, h2, p_sur, sdf, normal_out, face_idx);
-}
-
-// ---- 8 lanes per query: the neighbour search for K <= 8 (mesh_bvh.cuh, knn8_dynamic) ----------------------------------------------
-constexpr int kWarps8 = 2;                // warps per block; each warp owns one chunk of consecutive queries, its 4 groups pull from it
-constexpr int kThreads8 = kWarps8 * 32;
-constexpr int kMaxChunk8 = 256;
-
-// queries per warp: enough warps to fill the GPU (24 per SM) first, then up to 64 queries per group so that pulling evens out their cost
-static uint32_t chunk8_for(uint32_t N) {
-    const uint64_t target_warps = (uint64_t)device_sm_count() * 24;
-    const uint64_t per_warp = std::min<uint64_t>(kMaxChunk8, std::max<uint64_t>(32, N / target_warps));
-    return (uint32_t)(per_warp / 32 * 32);
-}
-
-__global__ void __launch_bounds__(kThreads8) mesh_knn8_kernel(uint32_t N, uint32_t chunk, const float* queries, float r2, int k_want,
-                                                              const Node8* __restrict__ nodes, float* dists, long long* idxs) {
-    __shared__ int ctr[kWarps8];
-    __shared__ uint2 stacks[kWarps8 * 4][kStack8];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t base64 = ((uint64_t)blockIdx.x * kWarps8 + warp) * chunk;
-    if (base64 >= N) return;   // warp-uniform
-    const uint32_t base = (uint32_t)base64;
-    const int n = (int)min(chunk, N - base);
-    if (lane == 0) ctr[warp] = 0;
-    __syncwarp();
-    knn8_dynamic(
-        nodes, n, r2, k_want, &ctr[warp], stacks[warp * 4 + (lane >> 3)], [&](int task, float* q) { load3(queries, base + task, q); },
-        [&](int task, const float*, float bd, int bi) {
-            const int j = (lane & 7) - (8 - k_want);   // lane s holds the s-th slot; the neighbours are the last k_want
-            if (j >= 0) {
-                const bool ok = knn_slot_valid(bi);
-                const size_t at = (size_t)(base + task) * k_want + j;
-                dists[at] = ok ? bd : -1.0f;
-                idxs[at] = ok ? bi : -1;
-            }
-        });
-}
-
-// tools/map.py:414-433 for one chunk of samples per warp:
-//   A  neighbour search, 8 lanes per sample; each lane forms the terms of ITS neighbour, a 3-step butterfly sums them, lane 0 of the
-//      group finishes the coarse normal -> shared memory
-//   B  one thread per sample: the two casts along +-normal (neighbouring lanes = neighbouring samples: coherent), select, store
-__global__ void __launch_bounds__(kThreads8) mesh_project8_kernel(uint32_t N, uint32_t chunk, const float* xyz, int k_want, float r2, float dir_vec_wdist,
-                                                                  const float* __restrict__ vertices, const float* __restrict__ vertex_normals,
-                                                                  uint32_t n_vertices, const Node8* __restrict__ pt_nodes,
-                                                                  const Node* __restrict__ tri_nodes, const Tri* __restrict__ tris, float slack,
-                                                                  float* p_sur, float* sdf, float* normal_out, long long* face_idx) {
-    __shared__ int ctr[kWarps8];
-    __shared__ uint2 stacks[kWarps8 * 4][kStack8];
-    __shared__ float s_normal[kWarps8][kMaxChunk8][3];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t base64 = ((uint64_t)blockIdx.x * kWarps8 + warp) * chunk;
-    if (base64 >= N) return;
-    const uint32_t base = (uint32_t)base64;
-    const int n = (int)min(chunk, N - base);
-    const unsigned gmask = 0xffu << (lane & ~7);
-    if (lane == 0) ctr[warp] = 0;
-    __syncwarp();
-    knn8_dynamic(
-        pt_nodes, n, r2, k_want, &ctr[warp], stacks[warp * 4 + (lane >> 3)], [&](int task, float* q) { load3(xyz, base + task, q); },
-        [&](int task, const float* q, float bd, int bi) {
-            float sums[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-            if ((lane & 7) >= 8 - k_want) neighbour_terms(q, knn_slot_valid(bi), bd, bi, vertices, vertex_normals, n_vertices, sums);
-#pragma unroll
-            for (int c = 0; c < 10; c++) {
-                sums[c] += __shfl_xor_sync(gmask, sums[c], 4);
-                sums[c] += __shfl_xor_sync(gmask, sums[c], 2);
-                sums[c] += __shfl_xor_sync(gmask, sums[c], 1);
-            }
-            if ((lane & 7) == 0) {
-                float nn[3];
-                finish_normal(sums, k_want, dir_vec_wdist, nn);
-                for (int c = 0; c < 3; c++) s_normal[warp][task][c] = nn[c];
-            }
-        });
-    __syncwarp();
-    for (int j = lane; j < n; j += 32) {
-        const size_t i = base + j;
-        float x[3], nrm[3], neg[3];
-        load3(xyz, (uint32_t)i, x);
-        for (int c = 0; c < 3; c++) { nrm[c] = s_normal[warp][j][c]; neg[c] = -nrm[c]; }
-        const Hit h1 = trace_one(tri_nodes, tris, x, nrm, slack);   // :419 inner
-        const Hit h2 = trace_one(tri_nodes, tris, x, neg, slack);   // :420 outer
-        project_outputs(i, x, nrm, h1, h2, p_sur, sdf, normal_out, face_idx);
-    }
 }
 
 static MeshHandle* checked(const void* mesh, const char* who) {
@@ -297,10 +208,6 @@ int ntx_mesh_create(const float* vertices, uint32_t n_vertices, const int32_t* t
     NTX_REQUIRE(build_triangle_tree(vertices, n_vertices, triangles, n_triangles, tri_tree, tris), NTX_ERR_INVALID_ARGUMENT,
                 "ntx_mesh_create: non-finite vertex or triangle index out of range");
     NTX_REQUIRE(build_point_tree(vertices, n_vertices, pt_tree, pts), NTX_ERR_INVALID_ARGUMENT, "ntx_mesh_create: non-finite vertex");
-    std::vector<Node8> nodes8;
-    int depth8 = 0;
-    NTX_REQUIRE(build_point_tree8(vertices, n_vertices, nodes8, depth8), NTX_ERR_INVALID_ARGUMENT, "ntx_mesh_create: non-finite vertex");
-    NTX_REQUIRE(7 * depth8 + 1 <= kStack8, NTX_ERR_UNSUPPORTED, "ntx_mesh_create: 8-wide tree deeper than its stack");
     NTX_REQUIRE(tri_tree.depth < kStackDepth && pt_tree.depth < kStackDepth, NTX_ERR_UNSUPPORTED, "ntx_mesh_create: tree deeper than %d", kStackDepth);
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (uint32_t i = 0; i < n_vertices; i++)
@@ -313,11 +220,9 @@ int ntx_mesh_create(const float* vertices, uint32_t n_vertices, const int32_t* t
     h->n_vertices = n_vertices; h->n_triangles = n_triangles;
     h->tri_nodes_n = (uint32_t)tri_tree.nodes.size(); h->pt_nodes_n = (uint32_t)pt_tree.nodes.size();
     h->tri_depth = tri_tree.depth; h->pt_depth = pt_tree.depth;
-    h->pt_nodes8_n = (uint32_t)nodes8.size(); h->pt_depth8 = (uint32_t)depth8;
     h->slack = 1e-5f * std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
     std::vector<float> verts(vertices, vertices + 3 * (size_t)n_vertices);
     const bool ok = upload(&h->tri_nodes, tri_tree.nodes) && upload(&h->tris, tris) && upload(&h->pt_nodes, pt_tree.nodes) && upload(&h->pts, pts) &&
-                    upload(&h->pt_nodes8, nodes8) &&
                     upload(&h->vertices, verts);
     if (!ok) {
         set_error("ntx_mesh_create: %s", cudaGetErrorString(cudaGetLastError()));
@@ -368,10 +273,7 @@ int ntx_mesh_knn(const void* mesh, const float* queries, uint32_t N, uint32_t K,
     cudaStream_t st = (cudaStream_t)stream;
     const float r2 = r * r;
     const dim3 grid(ceil_div(N, 128u));
-    if (K <= 8 && !tunables().mesh_thread_knn) {
-        const uint32_t chunk = chunk8_for(N);
-        mesh_knn8_kernel<<<ceil_div(N, chunk * kWarps8), kThreads8, 0, st>>>(N, chunk, queries, r2, (int)K, h->pt_nodes8, dists, (long long*)idxs);
-    } else if (K <= 8) {
+    if (K <= 8) {
         mesh_knn_kernel<8><<<grid, 128, 0, st>>>(N, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
     } else if (K <= 16) {
         mesh_knn_kernel<16><<<grid, 128, 0, st>>>(N, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
@@ -393,12 +295,7 @@ int ntx_mesh_project(const void* mesh, const float* vertex_normals, const float*
     cudaStream_t st = (cudaStream_t)stream;
     const float r2 = r * r;
     const dim3 grid(ceil_div(N, 128u));
-    if (K <= 8 && !tunables().mesh_thread_knn) {
-        const uint32_t chunk = chunk8_for(N);
-        mesh_project8_kernel<<<ceil_div(N, chunk * kWarps8), kThreads8, 0, st>>>(N, chunk, xyz, (int)K, r2, dir_vec_wdist, h->vertices, vertex_normals,
-                                                                                 h->n_vertices, h->pt_nodes8, h->tri_nodes, h->tris, h->slack, p_sur, sdf,
-                                                                                 normal, (long long*)face_idx);
-    } else if (K <= 8) {
+    if (K <= 8) {
         mesh_project_kernel<8><<<grid, 128, 0, st>>>(N, xyz, (int)K, r2, dir_vec_wdist, h->vertices, vertex_normals, h->n_vertices, h->pt_nodes, h->pts,
                                                      h->tri_nodes, h->tris, h->slack, p_sur, sdf, normal, (long long*)face_idx);
     } else {

@@ -212,86 +212,5 @@ inline bool build_point_tree(const float* points, uint32_t n_points, BuildResult
     return true;
 }
 
-// 8-wide vertex tree of mesh_bvh.cuh (Node8): a range of > 8 points is cut into ceil(n/8) (at most 8) nearly equal parts by repeated
-// object-median splits along the widest axis; a range of <= 8 points becomes a node whose entries are the points themselves.
-class Tree8Builder {
-public:
-    Tree8Builder(const float* points, uint32_t n) : p_(points), order_(n) {
-        for (uint32_t i = 0; i < n; i++) order_[i] = (int)i;
-    }
-    void run(std::vector<Node8>& nodes, int& depth) {
-        nodes_ = &nodes;
-        nodes.clear();
-        depth_ = 0;
-        build(0, (int)order_.size(), 1);
-        depth = depth_;
-    }
-
-private:
-    static void clear(Node8& nd) {
-        for (int s = 0; s < 8; s++) {
-            for (int k = 0; k < 3; k++) { nd.e[s].lo[k] = INFINITY; nd.e[s].hi[k] = -INFINITY; }
-            nd.e[s].link = kEntryEmpty;
-            nd.e[s].pad = 0;
-        }
-    }
-    void split(int begin, int end, int parts, std::vector<std::pair<int, int>>& out) {
-        if (parts <= 1) { out.emplace_back(begin, end); return; }
-        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-        for (int i = begin; i < end; i++)
-            for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], p_[3 * (size_t)order_[i] + k]); hi[k] = std::max(hi[k], p_[3 * (size_t)order_[i] + k]); }
-        int axis = 0;
-        for (int k = 1; k < 3; k++) if (hi[k] - lo[k] > hi[axis] - lo[axis]) axis = k;
-        const int pl = parts / 2;
-        const int mid = begin + (int)((int64_t)(end - begin) * pl / parts);
-        std::nth_element(order_.begin() + begin, order_.begin() + mid, order_.begin() + end, [&](int a, int b) {
-            const float ca = p_[3 * (size_t)a + axis], cb = p_[3 * (size_t)b + axis];
-            return ca < cb || (ca == cb && a < b);
-        });
-        split(begin, mid, pl, out);
-        split(mid, end, parts - pl, out);
-    }
-    int build(int begin, int end, int depth) {
-        depth_ = std::max(depth_, depth);
-        const int me = (int)nodes_->size();
-        nodes_->emplace_back();
-        clear((*nodes_)[me]);
-        const int count = end - begin;
-        if (count <= 8) {
-            for (int s = 0; s < count; s++) {
-                const int i = order_[begin + s];
-                Entry8& e = (*nodes_)[me].e[s];
-                for (int k = 0; k < 3; k++) e.lo[k] = e.hi[k] = p_[3 * (size_t)i + k];
-                e.link = ~i;
-            }
-            return me;
-        }
-        std::vector<std::pair<int, int>> parts;
-        split(begin, end, std::min(8, (count + 7) / 8), parts);
-        for (size_t s = 0; s < parts.size(); s++) {
-            const int b = parts[s].first, e = parts[s].second;
-            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-            for (int i = b; i < e; i++)
-                for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], p_[3 * (size_t)order_[i] + k]); hi[k] = std::max(hi[k], p_[3 * (size_t)order_[i] + k]); }
-            const int child = build(b, e, depth + 1);
-            Entry8& en = (*nodes_)[me].e[s];   // (after the recursion: the vector may have grown)
-            for (int k = 0; k < 3; k++) { en.lo[k] = lo[k]; en.hi[k] = hi[k]; }
-            en.link = child;
-        }
-        return me;
-    }
-
-    const float* p_;
-    std::vector<int> order_;
-    std::vector<Node8>* nodes_ = nullptr;
-    int depth_ = 0;
-};
-
-inline bool build_point_tree8(const float* points, uint32_t n_points, std::vector<Node8>& nodes, int& depth) {
-    for (uint64_t i = 0; i < (uint64_t)n_points * 3; i++) if (!std::isfinite(points[i])) return false;
-    Tree8Builder(points, n_points).run(nodes, depth);
-    return true;
-}
-
 }  // namespace mesh
 }  // namespace ntx

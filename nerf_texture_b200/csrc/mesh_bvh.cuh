@@ -10,7 +10,7 @@
 // round-to-nearest intrinsics (no FMA contraction) so that host restatement and kernel agree bit for bit.
 //
 // The traversal functions compile for host as well: tests/native/mesh_host_check.cpp instantiates them with g++ to check the tree
-// logic against exhaustive scans without a GPU.  The product library only ever runs them on the device.
+// logic against exhaustive scans without a GPU.  The product library only ever runs them on the device (csrc/mesh.cu).
 #pragma once
 
 #include <cfloat>
@@ -177,7 +177,7 @@ NTX_HD void trace_leaf_step(const Tri* tris, int link, const float* ro, const fl
     }
 }
 
-// One query, start to end (host check; the kernels pull queries dynamically, see *_dynamic below).
+// One query, start to end.
 NTX_HD Hit trace_one(const Node* nodes, const Tri* tris, const float* ro, const float* rd, float slack_abs) {
     Hit best{kMaxDist, -1, -1};
     const float inv[3] = {1.0f / rd[0], 1.0f / rd[1], 1.0f / rd[2]};
@@ -282,7 +282,7 @@ NTX_HD void knn_leaf_step(const Point* pts, int link, const float* q, float r2, 
     }
 }
 
-// One query, start to end (host check).  Returns the number of neighbours found (<= k_want); they are in slots K - k_want ...
+// One query, start to end.  Returns the number of neighbours found (<= k_want); they are in slots K - k_want ... K - 1.
 template <int K>
 NTX_HD int knn_one(const Node* nodes, const Point* pts, const float* q, float r2, int k_want, float* bd, int* bi) {
     knn_list_init<K>(bd, bi, k_want);
@@ -311,184 +311,6 @@ NTX_HD int knn_one(const Node* nodes, const Point* pts, const float* q, float r2
     for (int s = 0; s < K; s++) found += (s >= K - k_want) && knn_slot_valid(bi[s]);
     return found;
 }
-
-// ---------------------------------------------------------------------------------------------------------------------------
-// 8-wide tree over the mesh vertices for the neighbour search with K <= 8: 8 lanes share one query.
-//
-// One thread per query (knn_one above) is what a CPU would do and what the GPU does badly: queries differ 10x in cost and the
-// per-thread candidate list turns every accepted point into ~50 predicated instructions that only one lane of the warp needs —
-// measured on B200: 4.8 of 32 lanes active, 3.2 G warp instructions per 2^20 queries.  Here a node holds 8 ENTRIES of 32 bytes
-// (box + link), lane s of a group tests entry s, and a vertex is just an entry whose box is the point itself (lo = hi: the box
-// distance IS the point distance, bit for bit) — so there is a single kind of step, the same for every group of the warp:
-// pop -> 8 distances in parallel -> ballot -> insert accepted points into the list that lives ACROSS the 8 lanes (lane s holds the
-// s-th best; an insertion is one shuffle-up) -> push the surviving children, nearest on top.  Groups PULL queries from their warp's
-// chunk, so a group that finishes early starts the next query instead of waiting for the slowest of the warp.
-constexpr int kEntryEmpty = (int)0x80000000;   // link of an unused entry (box +inf/-inf: infinitely far)
-constexpr int kStack8 = 72;                    // >= 7 pushes per level + 1, 9 levels (2^27 points)
-
-struct alignas(32) Entry8 {   // link >= 0: child node; < 0: ~link = vertex index (lo = hi = the vertex); kEntryEmpty: unused
-    float lo[3], hi[3];
-    int link;
-    int pad;
-};
-struct alignas(256) Node8 {
-    Entry8 e[8];
-};
-static_assert(sizeof(Node8) == 256, "node8 layout");
-
-NTX_HD bool entry_is_point(int link) { return link < 0 && link != kEntryEmpty; }
-
-// Reference traversal of the 8-wide tree, one query, sequential (host check of the builder and of the pruning rules; the kernel
-// does the same steps with 8 lanes).  List layout as in knn_one: K = 8 slots, neighbours in the last k_want.
-NTX_HD int knn8_one(const Node8* nodes, const float* q, float r2, int k_want, float* bd, int* bi) {
-    knn_list_init<8>(bd, bi, k_want);
-    int stack_link[kStack8];
-    float stack_dist[kStack8];
-    int sp = 0;
-    stack_link[sp] = 0; stack_dist[sp] = 0.0f; sp++;
-    while (sp > 0) {
-        --sp;
-        const int node = stack_link[sp];
-        if (!(stack_dist[sp] <= bd[7])) continue;
-        float d2[8];
-        int link[8];
-        for (int s = 0; s < 8; s++) {
-            const Entry8& e = nodes[node].e[s];
-            d2[s] = box_sq_dist(e.lo, e.hi, q);
-            link[s] = e.link;
-        }
-        for (int s = 0; s < 8; s++) {   // points first (they tighten the bound the children are tested against)
-            if (!entry_is_point(link[s]) || !(d2[s] < r2)) continue;
-            const int idx = ~link[s];
-            if (!(d2[s] < bd[7] || (d2[s] == bd[7] && idx < bi[7]))) continue;
-            float cd = d2[s];
-            int ci = idx;
-            for (int k = 0; k < 8; k++) {
-                const bool before = cd < bd[k] || (cd == bd[k] && ci < bi[k]);
-                const float td = bd[k]; const int ti = bi[k];
-                bd[k] = before ? cd : td; bi[k] = before ? ci : ti;
-                cd = before ? td : cd; ci = before ? ti : ci;
-            }
-        }
-        // children that can still matter: slot order, except that the nearest goes last = on top
-        int order[8], n = 0, nearest = -1;
-        for (int s = 0; s < 8; s++)
-            if (link[s] >= 0 && d2[s] < r2 && d2[s] <= bd[7]) {
-                if (nearest < 0 || d2[s] < d2[nearest]) nearest = s;
-                order[n++] = s;
-            }
-        if (n > 1) {
-            int w = 0;
-            for (int i = 0; i < n; i++) if (order[i] != nearest) order[w++] = order[i];
-            order[w] = nearest;
-        }
-        for (int i = 0; i < n && sp < kStack8; i++) { stack_link[sp] = link[order[i]]; stack_dist[sp] = d2[order[i]]; sp++; }
-    }
-    int found = 0;
-    for (int s = 0; s < 8; s++) found += (s >= 8 - k_want) && knn_slot_valid(bi[s]);
-    return found;
-}
-
-#if defined(__CUDACC__)
-// Device form: the 32 lanes of a warp are 4 groups of 8; a group pulls queries from the warp's chunk (shared counter `ctr`) and runs
-// the steps above with lane s on entry s.  `stack` = this GROUP's kStack8 (link, distance) pairs in shared memory.
-//   load(task, q)            fills the query (every lane of the group gets the same q)
-//   emit(task, q, bd, bi)    called by all 8 lanes when the query is done: lane s holds the s-th best (slots 8 - k_want .. 7 are the
-//                            neighbours, ascending; an unused slot has bi == kEmptyIdx)
-// All 32 lanes must call this together.
-template <class Load, class Emit>
-__device__ __forceinline__ void knn8_dynamic(const Node8* __restrict__ nodes, int n_tasks, float r2, int k_want, int* ctr, uint2* stack, Load&& load,
-                                             Emit&& emit) {
-    const int lane = threadIdx.x & 31, s = lane & 7, g0 = lane & ~7;   // g0 = first lane of my group
-    const unsigned gmask = 0xffu << g0;
-    bool active = false, exhausted = false;
-    int task = 0, sp = 0;
-    float q[3] = {0.0f, 0.0f, 0.0f};
-    float bd = INFINITY;
-    int bi = kEmptyIdx;
-    for (;;) {
-        if (!active && !exhausted) {   // uniform within the group
-            int t = 0;
-            if (s == 0) t = atomicAdd(ctr, 1);
-            t = __shfl_sync(gmask, t, g0);
-            if (t < n_tasks) {
-                task = t;
-                load(task, q);
-                const bool filler = s < 8 - k_want;
-                bd = filler ? -1.0f : INFINITY;
-                bi = filler ? 0 : kEmptyIdx;
-                if (s == 0) stack[0] = make_uint2(0u, __float_as_uint(0.0f));   // the root
-                sp = 1;
-                active = true;
-                __syncwarp(gmask);
-            } else {
-                exhausted = true;
-            }
-        }
-        if (!__any_sync(0xffffffffu, active)) break;
-        if (active) {
-            --sp;
-            const uint2 top = stack[sp];
-            __syncwarp(gmask);   // everyone has read the top before anyone pushes over it
-            float worst = __shfl_sync(gmask, bd, g0 + 7);
-            int worst_i = __shfl_sync(gmask, bi, g0 + 7);
-            if (__uint_as_float(top.y) <= worst) {   // uniform within the group
-                const float4* ep = reinterpret_cast<const float4*>(&nodes[top.x].e[s]);
-                const float4 e0 = __ldg(ep), e1 = __ldg(ep + 1);
-                const float lo[3] = {e0.x, e0.y, e0.z}, hi[3] = {e0.w, e1.x, e1.y};
-                const int link = __float_as_int(e1.z);
-                const float d2 = box_sq_dist(lo, hi, q);
-                const bool in_range = d2 < r2;
-                // vertices of this node that beat the list
-                unsigned cm = __ballot_sync(gmask, in_range && entry_is_point(link) && (d2 < worst || (d2 == worst && ~link < worst_i))) & gmask;
-                while (cm) {   // uniform within the group
-                    const int src = __ffs(cm) - 1;
-                    cm &= cm - 1;
-                    const float cd = __shfl_sync(gmask, d2, src);
-                    const int ci = ~__shfl_sync(gmask, link, src);
-                    if (cd < worst || (cd == worst && ci < worst_i)) {   // still in after the insertions before it
-                        const bool before = cd < bd || (cd == bd && ci < bi);
-                        const float up_d = __shfl_up_sync(gmask, bd, 1, 8);
-                        const int up_i = __shfl_up_sync(gmask, bi, 1, 8);
-                        const int up_before = __shfl_up_sync(gmask, (int)before, 1, 8);
-                        if (before) {
-                            const bool shift = s > 0 && up_before;   // the lane above me moves down too: I take its entry, else the candidate lands here
-                            bd = shift ? up_d : cd;
-                            bi = shift ? up_i : ci;
-                        }
-                        worst = __shfl_sync(gmask, bd, g0 + 7);
-                        worst_i = __shfl_sync(gmask, bi, g0 + 7);
-                    }
-                }
-                // children that can still matter: the nearest goes on top of the stack, the others below it in slot order (measured on
-                // the host: 43.3 node visits per query against 42.1 for a full sort and 480 for no order at all)
-                const bool child = in_range && link >= 0 && d2 <= worst;
-                const unsigned chm = __ballot_sync(gmask, child) & gmask;
-                if (chm) {
-                    float key = child ? d2 : INFINITY;
-                    int kslot = s;
-#pragma unroll
-                    for (int off = 4; off > 0; off >>= 1) {
-                        const float od = __shfl_xor_sync(gmask, key, off);
-                        const int os = __shfl_xor_sync(gmask, kslot, off);
-                        if (od < key || (od == key && os < kslot)) { key = od; kslot = os; }
-                    }
-                    const int cnt = __popc(chm);
-                    const int below = __popc(chm & ((1u << lane) - 1u));
-                    const int pos = (s == kslot) ? cnt - 1 : below - (kslot < s ? 1 : 0);
-                    if (child && sp + pos < kStack8) stack[sp + pos] = make_uint2((unsigned)link, __float_as_uint(d2));
-                    sp = min(sp + cnt, kStack8);
-                }
-                __syncwarp(gmask);   // the pushes are visible to the whole group before the next pop
-            }
-            if (sp == 0) {
-                emit(task, q, bd, bi);
-                active = false;
-            }
-        }
-    }
-}
-#endif  // __CUDACC__
 
 }  // namespace mesh
 }  // namespace ntx

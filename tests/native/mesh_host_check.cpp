@@ -74,35 +74,4 @@ int hostcheck_knn(const float* points, uint32_t n_p, const float* queries, uint3
     return tree.depth;
 }
 
-// the 8-wide vertex tree (K <= 8): builder + the sequential form of the group traversal
-int hostcheck_knn8(const float* points, uint32_t n_p, const float* queries, uint32_t N, uint32_t K, float r, float* dists, int64_t* idxs, int64_t* stats) {
-    std::vector<Node8> nodes;
-    int depth = 0;
-    if (K > 8 || !build_point_tree8(points, n_p, nodes, depth)) return -1;
-    std::vector<int> seen(n_p, 0);
-    int64_t bad_box = 0;
-    for (const Node8& nd : nodes)
-        for (const Entry8& e : nd.e) {
-            if (entry_is_point(e.link)) seen[~e.link]++;
-            else if (e.link >= 0)
-                for (const Entry8& c : nodes[e.link].e)
-                    if (c.link != kEntryEmpty)
-                        for (int k = 0; k < 3; k++) bad_box += c.lo[k] < e.lo[k] || c.hi[k] > e.hi[k];
-        }
-    int64_t once = 0;
-    for (uint32_t i = 0; i < n_p; i++) once += seen[i] == 1;
-    stats[0] = (int64_t)nodes.size(); stats[1] = once; stats[2] = bad_box;
-    const float r2 = r * r;
-#pragma omp parallel for schedule(dynamic, 64)
-    for (int64_t i = 0; i < (int64_t)N; i++) {
-        float bd[8]; int bi[8];
-        const int found = knn8_one(nodes.data(), queries + 3 * i, r2, (int)K, bd, bi);
-        for (uint32_t s = 0; s < K; s++) {
-            dists[(size_t)i * K + s] = (int)s < found ? bd[8 - K + s] : -1.0f;
-            idxs[(size_t)i * K + s] = (int)s < found ? bi[8 - K + s] : -1;
-        }
-    }
-    return depth;
-}
-
 }

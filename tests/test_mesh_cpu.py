@@ -125,24 +125,6 @@ def test_host_knn_equals_exhaustive_scan(host, K, r):
     assert np.array_equal(_bits(hd), _bits(od)) and np.array_equal(hi, oi)
 
 
-@pytest.mark.parametrize("K,r", [(8, 100.0), (5, 100.0), (8, 0.3), (1, 100.0), (3, 0.2)])
-def test_host_knn_8wide_tree_equals_exhaustive_scan(host, K, r):
-    """the 8-lane-per-query tree of the K <= 8 kernels: every vertex in exactly one entry, child boxes inside their entry's box, and the
-    sequential form of the group traversal finds what the exhaustive scan finds"""
-    O = U.oracle()
-    rng = np.random.default_rng(10 + K)
-    for cloud in (U.bumpy_sphere(40, 60)[0], U.bumpy_sphere(3, 3)[0][:7], U.bumpy_sphere(3, 3)[0], U.bumpy_sphere(5, 13)[0],
-                  np.concatenate([np.round(rng.uniform(-1, 1, (2000, 3)) * 8) / 8] * 2).astype(np.float32)):
-        q = rng.uniform(-1, 1, (6000, 3)).astype(np.float32)
-        q[:2000] = np.round(q[:2000] * 16) / 16
-        od, oi = O.points_knn(cloud, q, K, r)
-        hd, hi = np.empty((len(q), K), np.float32), np.empty((len(q), K), np.int64)
-        st = np.zeros(3, np.int64)
-        depth = host.hostcheck_knn8(_p(cloud), len(cloud), _p(q), len(q), K, C.c_float(r), _p(hd), _p(hi), _p(st))
-        assert 1 <= depth <= 9 and st[1] == len(cloud) and st[2] == 0
-        assert np.array_equal(_bits(hd), _bits(od)) and np.array_equal(hi, oi)
-
-
 def test_host_knn_ties_duplicates_and_tiny_clouds(host):
     O = U.oracle()
     rng = np.random.default_rng(2)
