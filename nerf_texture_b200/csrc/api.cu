@@ -19,7 +19,6 @@ const Tunables& tunables() {
         v.field_ctas = (e = getenv("NTX_FIELD_CTAS")) ? atoi(e) : 0;
         v.pair_ctas = (e = getenv("NTX_PAIR_CTAS")) ? atoi(e) : 0;
         v.frame_ahead = (e = getenv("NTX_FRAME_AHEAD")) ? atoi(e) : 0;
-        v.mesh_node_loop = (e = getenv("NTX_MESH_NODE_LOOP")) ? atoi(e) : 0;
         return v;
     }();
     return t;

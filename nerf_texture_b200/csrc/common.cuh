@@ -26,7 +26,6 @@ void set_error(const char* fmt, ...);
 struct Tunables {
     int field_ctas;          // NTX_FIELD_CTAS: resident CTAs per SM of the fused field kernel (0 = as many as fit)
     int pair_ctas;           // NTX_PAIR_CTAS: same for the stand-alone pair gather kernel
-    int mesh_node_loop;      // NTX_MESH_NODE_LOOP=1: neighbour search walks inner nodes in a loop of their own (A/B, mesh.cu)
     int frame_ahead;         // NTX_FRAME_AHEAD: iterations ntx_render_rays queues ahead of the mailbox it has read (0 = by frame size)
 };
 const Tunables& tunables();

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128) mesh_trace_kernel(uint32_t N, const float
     for (int k = 0; k < 3; k++) normals[3 * (size_t)i + k] = n[k];
 }
 
-template <int K, bool kNodeLoop>
+template <int K>
 __global__ void __launch_bounds__(128) mesh_knn_kernel(uint32_t N, const float* queries, float r2, int k_want, const Node* __restrict__ nodes,
                                                        const Point* __restrict__ pts, float* dists, long long* idxs) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(128) mesh_knn_kernel(uint32_t N, const float* 
     load3(queries, i, q);
     float bd[K];
     int bi[K];
-    knn_one<K, kNodeLoop>(nodes, pts, q, r2, k_want, bd, bi);
+    knn_one<K>(nodes, pts, q, r2, k_want, bd, bi);
     const size_t row = (size_t)i * k_want;
 #pragma unroll
     for (int s = 0; s < K; s++) {
@@ -154,7 +154,7 @@ __device__ __forceinline__ void project_outputs(size_t i, const float* x, const 
 }
 
 // MeshProjector.project, one thread per sample: the neighbour list never leaves the registers, both casts run back to back
-template <int K, bool kNodeLoop>
+template <int K>
 __global__ void __launch_bounds__(128) mesh_project_kernel(uint32_t N, const float* xyz, int k_want, float r2, float dir_vec_wdist,
                                                            const float* __restrict__ vertices, const float* __restrict__ vertex_normals,
                                                            uint32_t n_vertices, const Node* __restrict__ pt_nodes, const Point* __restrict__ pts,
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(128) mesh_project_kernel(uint32_t N, const flo
     load3(xyz, i, x);
     float bd[K];
     int bi[K];
-    knn_one<K, kNodeLoop>(pt_nodes, pts, x, r2, k_want, bd, bi);
+    knn_one<K>(pt_nodes, pts, x, r2, k_want, bd, bi);
     float sums[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int s = 0; s < K; s++)
@@ -273,14 +273,12 @@ int ntx_mesh_knn(const void* mesh, const float* queries, uint32_t N, uint32_t K,
     cudaStream_t st = (cudaStream_t)stream;
     const float r2 = r * r;
     const dim3 grid(ceil_div(N, 128u));
-    if (K <= 8 && tunables().mesh_node_loop) {
-        mesh_knn_kernel<8, true><<<grid, 128, 0, st>>>(N, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
-    } else if (K <= 8) {
-        mesh_knn_kernel<8, false><<<grid, 128, 0, st>>>(N, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
+    if (K <= 8) {
+        mesh_knn_kernel<8><<<grid, 128, 0, st>>>(N, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
     } else if (K <= 16) {
-        mesh_knn_kernel<16, false><<<grid, 128, 0, st>>>(N, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
+        mesh_knn_kernel<16><<<grid, 128, 0, st>>>(N, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
     } else {
-        mesh_knn_kernel<32, false><<<grid, 128, 0, st>>>(N, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
+        mesh_knn_kernel<32><<<grid, 128, 0, st>>>(N, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
     }
     return check_launch("ntx_mesh_knn");
 }
@@ -297,14 +295,11 @@ int ntx_mesh_project(const void* mesh, const float* vertex_normals, const float*
     cudaStream_t st = (cudaStream_t)stream;
     const float r2 = r * r;
     const dim3 grid(ceil_div(N, 128u));
-    if (K <= 8 && tunables().mesh_node_loop) {
-        mesh_project_kernel<8, true><<<grid, 128, 0, st>>>(N, xyz, (int)K, r2, dir_vec_wdist, h->vertices, vertex_normals, h->n_vertices, h->pt_nodes, h->pts,
-                                                           h->tri_nodes, h->tris, h->slack, p_sur, sdf, normal, (long long*)face_idx);
-    } else if (K <= 8) {
-        mesh_project_kernel<8, false><<<grid, 128, 0, st>>>(N, xyz, (int)K, r2, dir_vec_wdist, h->vertices, vertex_normals, h->n_vertices, h->pt_nodes, h->pts,
+    if (K <= 8) {
+        mesh_project_kernel<8><<<grid, 128, 0, st>>>(N, xyz, (int)K, r2, dir_vec_wdist, h->vertices, vertex_normals, h->n_vertices, h->pt_nodes, h->pts,
                                                      h->tri_nodes, h->tris, h->slack, p_sur, sdf, normal, (long long*)face_idx);
     } else {
-        mesh_project_kernel<16, false><<<grid, 128, 0, st>>>(N, xyz, (int)K, r2, dir_vec_wdist, h->vertices, vertex_normals, h->n_vertices, h->pt_nodes, h->pts,
+        mesh_project_kernel<16><<<grid, 128, 0, st>>>(N, xyz, (int)K, r2, dir_vec_wdist, h->vertices, vertex_normals, h->n_vertices, h->pt_nodes, h->pts,
                                                       h->tri_nodes, h->tris, h->slack, p_sur, sdf, normal, (long long*)face_idx);
     }
     return check_launch("ntx_mesh_project");

@@ -260,48 +260,17 @@ NTX_HD int knn_node_step(const Node& nd, const float* q, float r2, float worst, 
     return (e0 < r2 && e0 <= worst) + (e1 < r2 && e1 <= worst);
 }
 
-NTX_HD int lowest_bit(unsigned m) {
-#if defined(__CUDA_ARCH__)
-    return __ffs((int)m) - 1;
-#else
-    return __builtin_ffs((int)m) - 1;
-#endif
-}
-
-// Leaf: all (<= 8) distances first — the loads go out together — then only the points that beat the list are inserted, one per
-// trip of a loop whose length is the number of accepted points.  In a warp every lane scans a different leaf: with the test and the
-// insertion interleaved per point, the ~50-instruction insertion ran for (almost) every point because SOME lane needed it; compacted,
-// it runs max-over-lanes(accepted points) times per leaf, typically 2-3 instead of 8.
 template <int K>
 NTX_HD void knn_leaf_step(const Point* pts, int link, const float* q, float r2, float* bd, int* bi) {
     const int first = leaf_first(link), count = leaf_count(link);
-    float d2[kPointLeafMax];
-    int id[kPointLeafMax];
-    unsigned accepted = 0;
-#pragma unroll
-    for (int i = 0; i < kPointLeafMax; i++) {
-        d2[i] = INFINITY;
-        id[i] = kEmptyIdx;
-        if (i < count) {
-            Point p;
-            fetch_point(pts, first + i, p);
-            d2[i] = sq_dist3(NTX_SUB(q[0], p.p[0]), NTX_SUB(q[1], p.p[1]), NTX_SUB(q[2], p.p[2]));
-            id[i] = p.idx;
-            const bool in = d2[i] < r2 && (d2[i] < bd[K - 1] || (d2[i] == bd[K - 1] && id[i] < bi[K - 1]));
-            accepted |= in ? (1u << i) : 0u;
-        }
-    }
-    while (accepted) {
-        const int i = lowest_bit(accepted);
-        accepted &= accepted - 1;
-        float cd = d2[0];
-        int ci = id[0];
-#pragma unroll
-        for (int j = 1; j < kPointLeafMax; j++) {   // d2[i] / id[i] without dynamic register indexing
-            cd = (i == j) ? d2[j] : cd;
-            ci = (i == j) ? id[j] : ci;
-        }
-        if (!(cd < bd[K - 1] || (cd == bd[K - 1] && ci < bi[K - 1]))) continue;   // an earlier point of this leaf pushed it out again
+    for (int i = 0; i < count; i++) {
+        Point p;
+        fetch_point(pts, first + i, p);
+        const float d2 = sq_dist3(NTX_SUB(q[0], p.p[0]), NTX_SUB(q[1], p.p[1]), NTX_SUB(q[2], p.p[2]));
+        if (!(d2 < r2)) continue;
+        if (!(d2 < bd[K - 1] || (d2 == bd[K - 1] && p.idx < bi[K - 1]))) continue;
+        float cd = d2;
+        int ci = p.idx;
 #pragma unroll
         for (int s = 0; s < K; s++) {   // sorted insertion: the carried entry sinks to its slot, the rest shift down, the last falls out
             const bool before = cd < bd[s] || (cd == bd[s] && ci < bi[s]);
@@ -314,54 +283,28 @@ NTX_HD void knn_leaf_step(const Point* pts, int link, const float* q, float r2, 
 }
 
 // One query, start to end.  Returns the number of neighbours found (<= k_want); they are in slots K - k_want ... K - 1.
-template <int K, bool kNodeLoop = false>
+template <int K>
 NTX_HD int knn_one(const Node* nodes, const Point* pts, const float* q, float r2, int k_want, float* bd, int* bi) {
     knn_list_init<K>(bd, bi, k_want);
     int stack[kStackDepth];
     int sp = 0;
     int cur = 0;
-    if (kNodeLoop) {
-        // inner nodes in a loop of their own: in a warp, lanes that reached a leaf wait here for the others, then all scan leaves together
-        for (;;) {
-            bool done = false;
-            while (cur >= 0) {
-                Node nd;
-                fetch_node(nodes, cur, nd);
-                int c_near, c_far;
-                const int n = knn_node_step(nd, q, r2, bd[K - 1], &c_near, &c_far);
-                if (n > 0) {
-                    cur = c_near;
-                    if (n > 1 && sp < kStackDepth) stack[sp++] = c_far;
-                } else if (sp > 0) {
-                    cur = stack[--sp];
-                } else {
-                    done = true;
-                    break;
-                }
+    for (;;) {
+        if (cur >= 0) {
+            Node nd;
+            fetch_node(nodes, cur, nd);
+            int c_near, c_far;
+            const int n = knn_node_step(nd, q, r2, bd[K - 1], &c_near, &c_far);
+            if (n > 0) {
+                cur = c_near;
+                if (n > 1 && sp < kStackDepth) stack[sp++] = c_far;
+                continue;
             }
-            if (done) break;
+        } else {
             knn_leaf_step<K>(pts, cur, q, r2, bd, bi);
-            if (sp == 0) break;
-            cur = stack[--sp];
         }
-    } else {
-        for (;;) {
-            if (cur >= 0) {
-                Node nd;
-                fetch_node(nodes, cur, nd);
-                int c_near, c_far;
-                const int n = knn_node_step(nd, q, r2, bd[K - 1], &c_near, &c_far);
-                if (n > 0) {
-                    cur = c_near;
-                    if (n > 1 && sp < kStackDepth) stack[sp++] = c_far;
-                    continue;
-                }
-            } else {
-                knn_leaf_step<K>(pts, cur, q, r2, bd, bi);
-            }
-            if (sp == 0) break;   // a popped subtree is re-tested against the current list when its node is fetched
-            cur = stack[--sp];
-        }
+        if (sp == 0) break;   // a popped subtree is re-tested against the current list when its node is fetched
+        cur = stack[--sp];
     }
     int found = 0;
 #pragma unroll
