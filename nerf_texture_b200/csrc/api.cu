@@ -19,6 +19,7 @@ const Tunables& tunables() {
         v.field_ctas = (e = getenv("NTX_FIELD_CTAS")) ? atoi(e) : 0;
         v.pair_ctas = (e = getenv("NTX_PAIR_CTAS")) ? atoi(e) : 0;
         v.frame_ahead = (e = getenv("NTX_FRAME_AHEAD")) ? atoi(e) : 0;
+        v.mesh_block = (e = getenv("NTX_MESH_BLOCK")) ? std::min(128, std::max(32, atoi(e) / 32 * 32)) : 128;
         return v;
     }();
     return t;

@@ -26,6 +26,7 @@ void set_error(const char* fmt, ...);
 struct Tunables {
     int field_ctas;          // NTX_FIELD_CTAS: resident CTAs per SM of the fused field kernel (0 = as many as fit)
     int pair_ctas;           // NTX_PAIR_CTAS: same for the stand-alone pair gather kernel
+    int mesh_block;          // NTX_MESH_BLOCK: threads per block of the mesh kernels (32..128, default 128)
     int frame_ahead;         // NTX_FRAME_AHEAD: iterations ntx_render_rays queues ahead of the mailbox it has read (0 = by frame size)
 };
 const Tunables& tunables();

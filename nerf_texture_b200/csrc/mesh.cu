@@ -258,7 +258,8 @@ int ntx_mesh_trace(const void* mesh, const float* rays_o, const float* rays_d, f
     if (!h) return NTX_ERR_INVALID_ARGUMENT;
     if (N == 0) return NTX_OK;
     NTX_REQUIRE(rays_o && rays_d && positions && normals && depth && face_idx, NTX_ERR_INVALID_ARGUMENT, "ntx_mesh_trace: null pointer");
-    mesh_trace_kernel<<<ceil_div(N, 128u), 128, 0, (cudaStream_t)stream>>>(N, rays_o, rays_d, positions, normals, depth, (long long*)face_idx,
+    const uint32_t block = (uint32_t)tunables().mesh_block;
+    mesh_trace_kernel<<<ceil_div(N, block), block, 0, (cudaStream_t)stream>>>(N, rays_o, rays_d, positions, normals, depth, (long long*)face_idx,
                                                                           h->tri_nodes, h->tris, h->slack);
     return check_launch("ntx_mesh_trace");
 }
@@ -272,13 +273,14 @@ int ntx_mesh_knn(const void* mesh, const float* queries, uint32_t N, uint32_t K,
     NTX_REQUIRE(queries && dists && idxs, NTX_ERR_INVALID_ARGUMENT, "ntx_mesh_knn: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const float r2 = r * r;
-    const dim3 grid(ceil_div(N, 128u));
+    const uint32_t block = (uint32_t)tunables().mesh_block;
+    const dim3 grid(ceil_div(N, block));
     if (K <= 8) {
-        mesh_knn_kernel<8><<<grid, 128, 0, st>>>(N, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
+        mesh_knn_kernel<8><<<grid, block, 0, st>>>(N, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
     } else if (K <= 16) {
-        mesh_knn_kernel<16><<<grid, 128, 0, st>>>(N, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
+        mesh_knn_kernel<16><<<grid, block, 0, st>>>(N, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
     } else {
-        mesh_knn_kernel<32><<<grid, 128, 0, st>>>(N, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
+        mesh_knn_kernel<32><<<grid, block, 0, st>>>(N, queries, r2, (int)K, h->pt_nodes, h->pts, dists, (long long*)idxs);
     }
     return check_launch("ntx_mesh_knn");
 }
@@ -294,12 +296,13 @@ int ntx_mesh_project(const void* mesh, const float* vertex_normals, const float*
     NTX_REQUIRE(vertex_normals && xyz && p_sur && sdf && normal && face_idx, NTX_ERR_INVALID_ARGUMENT, "ntx_mesh_project: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const float r2 = r * r;
-    const dim3 grid(ceil_div(N, 128u));
+    const uint32_t block = (uint32_t)tunables().mesh_block;
+    const dim3 grid(ceil_div(N, block));
     if (K <= 8) {
-        mesh_project_kernel<8><<<grid, 128, 0, st>>>(N, xyz, (int)K, r2, dir_vec_wdist, h->vertices, vertex_normals, h->n_vertices, h->pt_nodes, h->pts,
+        mesh_project_kernel<8><<<grid, block, 0, st>>>(N, xyz, (int)K, r2, dir_vec_wdist, h->vertices, vertex_normals, h->n_vertices, h->pt_nodes, h->pts,
                                                      h->tri_nodes, h->tris, h->slack, p_sur, sdf, normal, (long long*)face_idx);
     } else {
-        mesh_project_kernel<16><<<grid, 128, 0, st>>>(N, xyz, (int)K, r2, dir_vec_wdist, h->vertices, vertex_normals, h->n_vertices, h->pt_nodes, h->pts,
+        mesh_project_kernel<16><<<grid, block, 0, st>>>(N, xyz, (int)K, r2, dir_vec_wdist, h->vertices, vertex_normals, h->n_vertices, h->pt_nodes, h->pts,
                                                       h->tri_nodes, h->tris, h->slack, p_sur, sdf, normal, (long long*)face_idx);
     }
     return check_launch("ntx_mesh_project");
