@@ -168,19 +168,19 @@ def test_project_against_oracle(sphere):
     assert (fi >= 0).float().mean() > 0.95
 
 
-def test_unmodified_meshprojector_project_on_the_dropins(sphere):
-    """the reference's own tools/map.py, byte for byte: MeshProjector.project / .knn (map.py:414-500) run on the drop-in frnn and
-    RayTracer packages, and agree with the fused one-launch projection"""
+def _reference_map():
     sys.path.insert(0, os.path.join(U.ROOT, "tools"))
     import run_reference_files as R
     if not os.path.exists(os.path.join(R.STAGE, "callers", "tools", "map.py")):
         pytest.skip("reference files not staged (tools/stage_reference.py)")
-    ref_map = R.import_reference_map()
+    return R.import_reference_map()
+
+
+def _reference_projector(ref_map, v, f, vn):
+    """a MeshProjector of the reference's own class with the state its __init__ (trimesh / open3d / xatlas work) would leave behind"""
     import frnn
     from RayTracer import RayTracer
-    from nerf_texture_b200 import mesh as M
-    v, f, vn, _ = sphere
-    mp = ref_map.MeshProjector.__new__(ref_map.MeshProjector)           # __init__ is trimesh / open3d / xatlas work; these are its results
+    mp = ref_map.MeshProjector.__new__(ref_map.MeshProjector)
     mp.mesh_vertices, mp.vertex_normals = _t(v), _t(vn)
     _, _, _, mp.grid = frnn.frnn_grid_points(mp.mesh_vertices.unsqueeze(0), mp.mesh_vertices.unsqueeze(0), None, None, K=8, r=100., grid=None,
                                              return_nn=False, return_sorted=True)                                  # map.py:396
@@ -189,9 +189,24 @@ def test_unmodified_meshprojector_project_on_the_dropins(sphere):
     mp.faces = _t(f.astype(np.int64))
     g = torch.Generator().manual_seed(0)
     mp.tbn = torch.randn(len(f), 3, 3, generator=g).to(DEV)
-    rng = np.random.default_rng(11)
-    x = rng.normal(size=(30000, 3))
-    x = _t((x / np.linalg.norm(x, axis=1, keepdims=True) * rng.uniform(0.4, 1.0, (30000, 1))).astype(np.float32))
+    mp.uvs = None
+    return mp
+
+
+def _shell_samples(n, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(size=(n, 3))
+    return _t((x / np.linalg.norm(x, axis=1, keepdims=True) * rng.uniform(0.4, 1.0, (n, 1))).astype(np.float32))
+
+
+def test_unmodified_meshprojector_project_on_the_dropins(sphere):
+    """the reference's own tools/map.py, byte for byte: MeshProjector.project / .knn (map.py:414-500) run on the drop-in frnn and
+    RayTracer packages, and agree with the fused one-launch projection"""
+    ref_map = _reference_map()
+    from nerf_texture_b200 import mesh as M
+    v, f, vn, _ = sphere
+    mp = _reference_projector(ref_map, v, f, vn)
+    x = _shell_samples(30000, 11)
     p_sur, sdf, h_mask, normal, tbn = mp.project(x, K=8, h_threshold=0.1)                                          # the reference's code
     q_sur, qsdf, qmask, qnormal, qtbn = M.project(mp, x, K=8, h_threshold=0.1)                                     # one kernel
     assert qsdf.shape == sdf.shape and qmask.shape == h_mask.shape and qtbn.shape == tbn.shape
@@ -205,6 +220,40 @@ def test_unmodified_meshprojector_project_on_the_dropins(sphere):
     assert agree > 0.999
     same = (qtbn == tbn).all(-1).all(-1).float().mean().item()
     assert same > 0.998
+
+
+def test_unmodified_texture_field_runs_end_to_end(sphere):
+    """SURVEY 8 f3's purpose: the PRODUCT's field — the reference's unmodified MeshFeatureField (tools/map.py:546; cfgT hash grids, mesh
+    projection, factorised normal net) — constructs and evaluates on the drop-in packages alone (gridencoder, frnn, RayTracer), and gives
+    the same embedding with the projection swapped for the fused kernel"""
+    ref_map = _reference_map()
+    from nerf_texture_b200 import mesh as M
+    v, f, vn, _ = sphere
+    mp = _reference_projector(ref_map, v, f, vn)
+    original = ref_map.MeshProjector
+    ref_map.MeshProjector = lambda *a, **k: mp          # MeshFeatureField.__init__ builds its projector from a mesh FILE (trimesh): hand it ours
+    try:
+        torch.manual_seed(0)
+        field = ref_map.MeshFeatureField(mesh_path=None, h_threshold=0.1, K=8, bound=1).to(DEV)
+    finally:
+        ref_map.MeshProjector = original
+    with torch.no_grad():
+        field.encoder.embeddings.uniform_(-1, 1)        # the reference initialises to +-1e-4: make the features worth comparing
+    x = _shell_samples(20000, 21)
+    with torch.no_grad():
+        embed, n_coarse, n_fine, h_mask = field(x, no_noise=True)                                 # map.py:621: project -> encoders -> normal net
+    assert embed.shape == (20000, field.encoder_f_out_dim + field.encoder_z_outdim) and n_coarse.shape == (20000, 3) and n_fine.shape == (20000, 3)
+    assert h_mask.dtype == torch.bool and 0.1 < h_mask.float().mean().item() < 0.9
+    assert torch.isfinite(embed[h_mask]).all() and torch.isfinite(n_fine[h_mask]).all()
+    mp.project = lambda xyz, K=8, h_threshold=None, requires_grad_xyz=False, use_dir_vec=True: M.project(mp, xyz, K=K, h_threshold=h_threshold)
+    with torch.no_grad():
+        embed2, n_coarse2, n_fine2, h_mask2 = field(x, no_noise=True)
+    assert (h_mask == h_mask2).float().mean().item() > 0.999
+    both = h_mask & h_mask2
+    assert (n_coarse - n_coarse2).abs().max().item() < 1e-4
+    # p_sur moves by <= 1e-4 only where both projections landed on the same face; the hash-grid features are continuous in p_sur
+    close = ((embed - embed2).abs().max(dim=1)[0] < 2e-2) & ((n_fine - n_fine2).abs().max(dim=1)[0] < 2e-2)
+    assert close[both].float().mean().item() > 0.995
 
 
 def test_full_size_properties():

@@ -7,6 +7,8 @@
   * `project_fused`: the whole projection as ONE kernel (ntx_mesh_project),
   * `project_reference_chain`: the reference's UNMODIFIED MeshProjector.project (staged tools/map.py) on the drop-in `frnn` and
     `RayTracer` packages — the same searches, but ~30 torch kernels over [N,K,3] temporaries in between,
+  * `texture_field_forward_*`: the reference's unmodified `MeshFeatureField.forward` (the product's field, cfgT grids) on the drop-ins, with
+    its own projection chain and with the fused projection,
   * `cpu`: the oracle's exhaustive-scan restatement on the host cores, on a bounded sample of the same batch.
 
 Samples: 8192 camera-like rays x 128 steps through the shell 0.45 <= |x| <= 0.95 around a 230 K-triangle bumpy sphere, in ray order
@@ -104,6 +106,23 @@ def main():
             res["project_reference_chain_ms"] = timed(lambda: mp.project(x, K=8, h_threshold=0.1))            # the reference's code on the drop-ins
             res["project_fused_same_outputs_ms"] = timed(lambda: M.project(mp, x, K=8, h_threshold=0.1))     # one kernel + tbn gather + h_mask
             res["fused_vs_chain"] = res["project_reference_chain_ms"] / res["project_fused_same_outputs_ms"]
+            # the product's field: the reference's unmodified MeshFeatureField.forward (map.py:621: projection -> two cfgT hash-grid encodes ->
+            # frequency encoding of the sdf -> factorised normal net) on the drop-in packages, then with only the projection swapped
+            original = ref_map.MeshProjector
+            ref_map.MeshProjector = lambda *a, **k: mp
+            try:
+                torch.manual_seed(0)
+                field = ref_map.MeshFeatureField(mesh_path=None, h_threshold=0.1, K=8, bound=1).to(dev)
+            finally:
+                ref_map.MeshProjector = original
+
+            def field_forward():
+                with torch.no_grad():
+                    field(x, no_noise=True)
+            res["texture_field_forward_reference_chain_ms"] = timed(field_forward)
+            mp.project = lambda xyz, K=8, h_threshold=None, requires_grad_xyz=False, use_dir_vec=True: M.project(mp, xyz, K=K, h_threshold=h_threshold)
+            res["texture_field_forward_fused_projection_ms"] = timed(field_forward)
+            del mp.project
         except Exception as e:
             res["project_reference_chain_ms"] = {"unavailable": repr(e)[:300]}
 
