@@ -256,6 +256,53 @@ def test_unmodified_texture_field_runs_end_to_end(sphere):
     assert close[both].float().mean().item() > 0.995
 
 
+def test_products_model_renders_through_the_unmodified_renderer(sphere):
+    """the PRODUCT end to end: the reference's unmodified nerf/network_curvedfield.py model (texture field on a mesh, tcnn networks) builds
+    its occupancy grid with the unmodified NeRFRenderer.update_extra_state and renders a frame through the unmodified
+    NeRFRenderer.render -> run_cuda, all on the drop-in packages (gridencoder, tinycudann, raymarching, frnn, RayTracer); swapping the
+    projection for the fused kernel gives the same picture"""
+    sys.path.insert(0, os.path.join(U.ROOT, "tools"))
+    import run_reference_files as R
+    if not os.path.exists(os.path.join(R.STAGE, "callers", "nerf", "network_curvedfield.py")):
+        pytest.skip("reference files not staged (tools/stage_reference.py)")
+    ref_map, NeRFNetwork = R.import_reference_product_model()
+    from nerf_texture_b200 import mesh as M
+    from nerf_texture_b200 import scene
+    v, f, vn, _ = sphere
+    mp = _reference_projector(ref_map, v, f, vn)
+    original = ref_map.MeshProjector
+    ref_map.MeshProjector = lambda *a, **k: mp
+    try:
+        torch.manual_seed(0)
+        model = NeRFNetwork(surface_mesh_path=None, light_model="None", bound=1, cuda_ray=True).to(DEV).eval()     # network_curvedfield.py:33
+    finally:
+        ref_map.MeshProjector = original
+    with torch.no_grad():
+        model.meshfea_field.encoder.embeddings.uniform_(-1, 1)
+    rays_o, rays_d = scene.pinhole_rays(96, 96, torch.device(DEV))
+
+    def frame():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.half):
+            return model.render(rays_o[None], rays_d[None], staged=False, bg_color=1, perturb=False, max_steps=1024)
+
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.half):
+        model.update_extra_state()                                                              # renderer.py:567: density() of 128^3 cells -> bit-field
+    occupied = sum(bin(b).count("1") for b in model.density_bitfield.cpu().numpy().tobytes()) / (128.0 ** 3)
+    assert 0.01 < occupied < 0.6, occupied                                                      # the shell |sdf| < h_threshold around the mesh
+    out = frame()
+    image, depth = out["image"][0].float(), out["depth"][0].float()
+    assert image.shape == (96 * 96, 3) and torch.isfinite(image).all() and torch.isfinite(depth).all()
+    b = (rays_o * rays_d).sum(-1)
+    hits_ball = (b * b - ((rays_o * rays_o).sum(-1) - 0.55 ** 2)) > 0                           # rays through the inside of the bumpy sphere (r >= 0.6)
+    far_miss = (b * b - ((rays_o * rays_o).sum(-1) - 0.95 ** 2)) < 0                            # rays that pass outside the shell altogether
+    assert (image[far_miss] == 1).all() and (depth[far_miss] == 0).all()                        # background only
+    assert (image[hits_ball] < 0.999).any(dim=-1).float().mean() > 0.95                         # the shell absorbs something on every such ray
+    mp.project = lambda xyz, K=8, h_threshold=None, requires_grad_xyz=False, use_dir_vec=True: M.project(mp, xyz, K=K, h_threshold=h_threshold)
+    out2 = frame()
+    diff = (out2["image"][0].float() - image).abs()
+    assert diff.max().item() < 5e-2 and diff.mean().item() < 1e-3, (diff.max().item(), diff.mean().item())
+
+
 def test_full_size_properties():
     """BASELINE-size batch (2^22 samples, 230 K triangles): properties that need no exhaustive scan"""
     from nerf_texture_b200.mesh import Mesh

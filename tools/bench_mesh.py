@@ -123,6 +123,32 @@ def main():
             mp.project = lambda xyz, K=8, h_threshold=None, requires_grad_xyz=False, use_dir_vec=True: M.project(mp, xyz, K=K, h_threshold=h_threshold)
             res["texture_field_forward_fused_projection_ms"] = timed(field_forward)
             del mp.project
+            # the product's MODEL (nerf/network_curvedfield.py, unmodified) rendered by the unmodified NeRFRenderer on the drop-ins: a 512^2 frame
+            try:
+                from nerf_texture_b200 import scene
+                _, NeRFNetwork = R.import_reference_product_model()
+                ref_map.MeshProjector = lambda *a, **k: mp
+                try:
+                    torch.manual_seed(0)
+                    model = NeRFNetwork(surface_mesh_path=None, light_model="None", bound=1, cuda_ray=True).to(dev).eval()
+                finally:
+                    ref_map.MeshProjector = original
+                rays_o, rays_d = scene.pinhole_rays(512, 512, dev)
+
+                def frame():
+                    with torch.no_grad(), torch.autocast("cuda", dtype=torch.half):
+                        model.render(rays_o[None], rays_d[None], staged=False, bg_color=1, perturb=False, max_steps=1024)
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.half):
+                    t0 = time.time()
+                    model.update_extra_state()
+                    torch.cuda.synchronize()
+                    res["product_model_update_extra_state_s"] = round(time.time() - t0, 3)
+                res["product_model_frame_512_reference_chain_ms"] = timed(frame)
+                mp.project = lambda xyz, K=8, h_threshold=None, requires_grad_xyz=False, use_dir_vec=True: M.project(mp, xyz, K=K, h_threshold=h_threshold)
+                res["product_model_frame_512_fused_projection_ms"] = timed(frame)
+                del mp.project
+            except Exception as e:
+                res["product_model_frame_512_reference_chain_ms"] = {"unavailable": repr(e)[:300]}
         except Exception as e:
             res["project_reference_chain_ms"] = {"unavailable": repr(e)[:300]}
 

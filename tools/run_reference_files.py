@@ -139,6 +139,18 @@ def import_reference_map():
     return ref_map
 
 
+def import_reference_product_model():
+    """(tools.map module, NeRFNetwork of the reference's nerf/network_curvedfield.py — the PRODUCT's model: mesh-anchored texture field,
+    tcnn sigma / colour networks, SH direction encoding) over the drop-in packages"""
+    ref_map = import_reference_map()
+    if "nerf" not in sys.modules:
+        pkg = types.ModuleType("nerf")
+        pkg.__path__ = [os.path.join(STAGE, "callers", "nerf")]
+        sys.modules["nerf"] = pkg
+    from nerf.network_curvedfield import NeRFNetwork
+    return ref_map, NeRFNetwork
+
+
 def build_model(NeRFNetwork, device, seed=0):
     import torch
     sys.path.insert(0, ROOT)

@@ -8,7 +8,8 @@ like oracle/_ref/ (the reference's CUDA rebuilt for sm_100a).  Two trees are sta
 
   baseline/_ref/callers/   nerf/{renderer,network_ff,utils}.py, tools/{encoding,activation,shape_tools,map,__init__}.py
                            — the code that CALLS the hot path (renderer.py:338 run_cuda, network_ff.py:55 forward; map.py:414
-                           MeshProjector.project for the mesh front end);
+                           MeshProjector.project for the mesh front end; network_curvedfield.py
+                           + the light-model files it imports: the product's own model);
   baseline/_ref/wrappers/  gridencoder/, ffmlp/, shencoder/, raymarching/ *.py — the reference's own operator wrappers, used only
                            by the reference arm (on top of oracle/_ref/_ref_*.so) in tests/test_gpu_reference_files.py and bench.py.
 
@@ -23,7 +24,7 @@ REF = os.environ.get("NTX_REFERENCE_ROOT", "/root/reference")
 DST = os.path.join(ROOT, "baseline", "_ref")
 
 CALLERS = ["nerf/renderer.py", "nerf/network_ff.py", "nerf/utils.py", "tools/__init__.py", "tools/encoding.py", "tools/activation.py", "tools/shape_tools.py",
-           "tools/map.py"]
+           "tools/map.py", "nerf/network_curvedfield.py", "nerf/sg_light_model.py", "nerf/sh_light_model.py", "nerf/envmap_light_model.py"]
 WRAPPERS = ["gridencoder/__init__.py", "gridencoder/grid.py", "gridencoder/grid_clustering.py", "ffmlp/__init__.py", "ffmlp/ffmlp.py",
             "shencoder/__init__.py", "shencoder/sphere_harmonics.py", "raymarching/__init__.py", "raymarching/raymarching.py"]
 
