@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """SASS evidence of the Blackwell-native paths, taken from the built nerf_texture_b200/lib/libntx.so (no GPU needed):
 
-    python tools/dump_sass.py            # writes profiles/r02_sass_{field,mlp,mlp_bwd,raymarch,grid}.txt
+    python tools/dump_sass.py            # writes profiles/r02_sass_{field,mlp,mlp_bwd,raymarch,grid,mesh}.txt
 
 For every kernel of the object: registers (from the ptxas log), and how often the tcgen05 / TMEM / TMA / mbarrier mnemonics occur
 (`UTCHMMA` = tcgen05.mma — with `tmem[..]` as its first operand pair when A comes from tensor memory —, `LDTM`/`STTM` = tcgen05.ld/st,
@@ -16,7 +16,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "nerf_texture_b200", "lib", "obj")
 OUT = os.path.join(ROOT, "profiles")
-PAT = ["UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTCBAR", "SYNCS", "UTCATOMSWS", "HMMA", "RED", "ATOMS", "LDGSTS"]
+PAT = ["UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTCBAR", "SYNCS", "UTCATOMSWS", "HMMA", "RED", "ATOMS", "LDGSTS", "FMNMX3", "LDL", "STL", "LDG.E.128.CONSTANT"]
 
 
 def demangle(names):
@@ -26,7 +26,7 @@ def demangle(names):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    for unit in ("field", "mlp", "mlp_bwd", "raymarch", "grid"):
+    for unit in ("field", "mlp", "mlp_bwd", "raymarch", "grid", "mesh"):
         obj = os.path.join(OBJ, unit + ".o")
         if not os.path.exists(obj):
             print("missing", obj, "(run python -m nerf_texture_b200.build first)")
