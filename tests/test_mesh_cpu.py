@@ -151,3 +151,34 @@ def test_mesh_create_validates_before_touching_the_gpu():
     assert lib.ntx_mesh_create(None, 0, None, 0, C.byref(h)) == -1
     assert lib.ntx_mesh_trace(None, None, None, None, None, None, None, 4, None) == -1      # not a handle
     assert lib.ntx_mesh_destroy(None) == 0
+
+
+def test_trees_stay_shallow_and_exact_on_hostile_vertex_distributions(host):
+    """geometric progressions (every split isolates one primitive), a single line, all-equal points, huge coordinate ranges: the builder
+    must stay below the traversal stack (64) — ntx_mesh_create refuses deeper trees — and the searches must stay exact"""
+    O = U.oracle()
+    rng = np.random.default_rng(5)
+    n = 3000
+    geo = np.stack([2.0 ** -np.arange(n, dtype=np.float64) * 1e3, np.zeros(n), np.zeros(n)], 1)
+    geo[1500:, 0] = 0.0                                                   # half of them underflow to the same point
+    line = np.stack([np.linspace(-1, 1, n), np.zeros(n), np.zeros(n)], 1)
+    same = np.ones((n, 3)) * 0.25
+    wide = rng.uniform(-1, 1, (n, 3)) * np.array([1e6, 1e-6, 1.0])
+    q = rng.uniform(-1, 1, (3000, 3)).astype(np.float32)
+    for cloud in (geo, line, same, wide):
+        v = cloud.astype(np.float32)
+        f = np.stack([np.arange(n - 2), np.arange(1, n - 1), np.arange(2, n)], 1).astype(np.int32)   # a strip of (mostly degenerate) triangles
+        for points in (0, 1):
+            st = np.zeros(3, np.int64)
+            depth = host.hostcheck_tree(_p(v), n, _p(f), len(f), points, _p(st))
+            assert 1 <= depth < 64, depth
+            assert st[1] == (n if points else len(f)) and st[2] == 0
+        od, oi = O.points_knn(v, q, 8, 100.0)
+        hd, hi = np.empty((len(q), 8), np.float32), np.empty((len(q), 8), np.int64)
+        host.hostcheck_knn(_p(v), n, _p(q), len(q), 8, C.c_float(100.0), _p(hd), _p(hi))
+        assert np.array_equal(_bits(hd), _bits(od)) and np.array_equal(hi, oi)
+        o, d = U.random_rays(rng, 3000)
+        _, _, depth_o, face_o = O.mesh_trace(v, f, o, d)
+        gd, gf = np.empty(len(o), np.float32), np.empty(len(o), np.int64)
+        host.hostcheck_trace(_p(v), n, _p(f), len(f), _p(o), _p(d), len(o), C.c_float(1e-5), _p(gd), _p(gf))
+        assert np.array_equal(_bits(gd), _bits(depth_o)) and np.array_equal(gf, face_o)
