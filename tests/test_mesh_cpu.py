@@ -182,3 +182,32 @@ def test_trees_stay_shallow_and_exact_on_hostile_vertex_distributions(host):
         gd, gf = np.empty(len(o), np.float32), np.empty(len(o), np.int64)
         host.hostcheck_trace(_p(v), n, _p(f), len(f), _p(o), _p(d), len(o), C.c_float(1e-5), _p(gd), _p(gf))
         assert np.array_equal(_bits(gd), _bits(depth_o)) and np.array_equal(gf, face_o)
+
+
+def test_property_random_small_meshes_and_clouds(host):
+    """hypothesis: any small mesh / cloud (coordinates on a coarse lattice, so coincident vertices, coplanar and degenerate triangles, rays
+    through vertices and exact distance ties are common), any K and radius — tree search == exhaustive scan, bit for bit"""
+    from hypothesis import given, settings, strategies as st
+    O = U.oracle()
+
+    @settings(max_examples=60, deadline=None)
+    @given(seed=st.integers(0, 2 ** 31 - 1), n_v=st.integers(3, 40), n_t=st.integers(1, 60), K=st.integers(1, 8), lattice=st.sampled_from([2, 4, 64]),
+           r=st.sampled_from([0.25, 0.5, 1.0, 100.0]))
+    def check(seed, n_v, n_t, K, lattice, r):
+        rng = np.random.default_rng(seed)
+        v = (np.round(rng.uniform(-1, 1, (n_v, 3)) * lattice) / lattice).astype(np.float32)
+        f = rng.integers(0, n_v, (n_t, 3)).astype(np.int32)
+        o = (np.round(rng.uniform(-1.5, 1.5, (300, 3)) * lattice) / lattice).astype(np.float32)
+        tgt = v[rng.integers(0, n_v, 300)] + (rng.uniform(-0.1, 0.1, (300, 3)) * (rng.random((300, 1)) < 0.5)).astype(np.float32)
+        d = (tgt - o).astype(np.float32)
+        d[:50] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 50)]
+        _, _, depth_o, face_o = O.mesh_trace(v, f, o, d)
+        gd, gf = np.empty(300, np.float32), np.empty(300, np.int64)
+        assert host.hostcheck_trace(_p(v), n_v, _p(f), n_t, _p(o), _p(d), 300, C.c_float(1e-5), _p(gd), _p(gf)) > 0
+        assert np.array_equal(_bits(gd), _bits(depth_o)) and np.array_equal(gf, face_o)
+        od, oi = O.points_knn(v, o, K, r)
+        hd, hi = np.empty((300, K), np.float32), np.empty((300, K), np.int64)
+        assert host.hostcheck_knn(_p(v), n_v, _p(o), 300, K, C.c_float(r), _p(hd), _p(hi)) > 0
+        assert np.array_equal(_bits(hd), _bits(od)) and np.array_equal(hi, oi)
+
+    check()
