@@ -17,6 +17,28 @@ import torch
 from . import _lib as L
 
 _F32, _I64 = torch.float32, torch.int64
+SORT_MIN = 1 << 16      # batches at least this large are visited in Morton order of their positions (see spatial_order)
+
+
+def _spread3(v):
+    """10 bits -> every third bit of a 30-bit integer (int32 tensor arithmetic)"""
+    v = (v | (v << 16)) & 0x030000FF
+    v = (v | (v << 8)) & 0x0300F00F
+    v = (v | (v << 4)) & 0x030C30C3
+    v = (v | (v << 2)) & 0x09249249
+    return v
+
+
+def spatial_order(x):
+    """Permutation that visits the points x [N,3] along a 30-bit Morton curve of their own bounding box.
+
+    The mesh kernels run one thread per query and a warp costs what its slowest lane costs; queries that are neighbours in SPACE walk the
+    same tree nodes (lanes stay together, the nodes are in L1).  Samples arrive ordered by ray and step — neighbours in a warp are
+    then 10..100 leaf diameters apart.  Results do not depend on the order (every query is independent), only the time does."""
+    lo, hi = x.min(dim=0)[0], x.max(dim=0)[0]
+    g = ((x - lo) * (1023.0 / (hi - lo).clamp_min(1e-30))).clamp_(0, 1023).to(torch.int32)
+    code = _spread3(g[:, 0]) | (_spread3(g[:, 1]) << 1) | (_spread3(g[:, 2]) << 2)
+    return torch.sort(code)[1]
 
 
 class Mesh:
@@ -69,20 +91,27 @@ class Mesh:
                    L.ptr(face_idx, _I64), N, L.stream())
         return positions.view(*prefix, 3), normals.view(*prefix, 3), depth.view(*prefix), face_idx
 
-    def knn(self, queries, K=8, r=100.0):
-        """K nearest mesh vertices within r: squared dists [..., K] f32 ascending, idxs [..., K] i64; -1 padding."""
+    def knn(self, queries, K=8, r=100.0, sort=None):
+        """K nearest mesh vertices within r: squared dists [..., K] f32 ascending, idxs [..., K] i64; -1 padding.
+        sort: visit the queries in Morton order (None = for batches of SORT_MIN or more); the results are the same either way."""
         q = self._dev(queries)
         prefix = q.shape[:-1]
         q = q.view(-1, 3)
         N = q.shape[0]
+        order = spatial_order(q) if (N >= SORT_MIN if sort is None else (sort and N > 1)) else None
+        if order is not None:
+            q = q[order]
         dists = torch.empty(N, K, dtype=_F32, device=self.device)
         idxs = torch.empty(N, K, dtype=_I64, device=self.device)
         with torch.cuda.device(self.device):
             L.call("ntx_mesh_knn", self._h, L.ptr(q, _F32), N, int(K), float(r), L.ptr(dists, _F32), L.ptr(idxs, _I64), L.stream())
+        if order is not None:
+            dists, idxs = torch.empty_like(dists).index_copy_(0, order, dists), torch.empty_like(idxs).index_copy_(0, order, idxs)
         return dists.view(*prefix, K), idxs.view(*prefix, K)
 
-    def project(self, xyz, vertex_normals, K=8, r=100.0, dir_vec_wdist=0.05):
-        """MeshProjector.project (tools/map.py:414-433) without its tbn gather / h_mask: p_sur [...,3], sdf [...,1], normal [...,3], face_idx [...]."""
+    def project(self, xyz, vertex_normals, K=8, r=100.0, dir_vec_wdist=0.05, sort=None):
+        """MeshProjector.project (tools/map.py:414-433) without its tbn gather / h_mask: p_sur [...,3], sdf [...,1], normal [...,3], face_idx [...].
+        sort: as in knn()."""
         x = self._dev(xyz)
         vn = self._dev(vertex_normals)
         if vn.shape != (self.n_vertices, 3):
@@ -90,12 +119,18 @@ class Mesh:
         prefix = x.shape[:-1]
         x = x.view(-1, 3)
         N = x.shape[0]
+        order = spatial_order(x) if (N >= SORT_MIN if sort is None else (sort and N > 1)) else None
+        if order is not None:
+            x = x[order]
         p_sur, normal = torch.empty_like(x), torch.empty_like(x)
         sdf = torch.empty(N, dtype=_F32, device=self.device)
         face_idx = torch.empty(N, dtype=_I64, device=self.device)
         with torch.cuda.device(self.device):
             L.call("ntx_mesh_project", self._h, L.ptr(vn, _F32), L.ptr(x, _F32), N, int(K), float(r), float(dir_vec_wdist), L.ptr(p_sur, _F32),
                    L.ptr(sdf, _F32), L.ptr(normal, _F32), L.ptr(face_idx, _I64), L.stream())
+        if order is not None:
+            p_sur, normal = torch.empty_like(p_sur).index_copy_(0, order, p_sur), torch.empty_like(normal).index_copy_(0, order, normal)
+            sdf, face_idx = torch.empty_like(sdf).index_copy_(0, order, sdf), torch.empty_like(face_idx).index_copy_(0, order, face_idx)
         return p_sur.view(*prefix, 3), sdf.view(*prefix, 1), normal.view(*prefix, 3), face_idx.view(*prefix)
 
 

@@ -304,6 +304,22 @@ def test_products_model_renders_through_the_unmodified_renderer(sphere):
     assert diff.max().item() < 0.1 and diff.mean().item() < 1e-2, (diff.max().item(), diff.mean().item())
 
 
+def test_morton_visit_order_changes_nothing(sphere):
+    """large batches are visited in Morton order of their positions (mesh.spatial_order): same bits out, in the caller's order"""
+    v, f, vn, mesh = sphere
+    x = _shell_samples(150000, 31)
+    a = mesh.knn(x, K=8, sort=False)
+    b = mesh.knn(x, K=8, sort=True)
+    c = mesh.knn(x, K=8)                                     # default: sorted from mesh.SORT_MIN queries on
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
+    pa = mesh.project(x, _t(vn), K=8, sort=False)
+    pb = mesh.project(x, _t(vn), K=8, sort=True)
+    for u, w in zip(pa, pb):
+        assert torch.equal(u, w)
+    few = mesh.project(x[:1], _t(vn), K=8, sort=True)        # a single sample cannot be ordered
+    assert torch.equal(few[1], pa[1][:1])
+
+
 def test_full_size_properties():
     """BASELINE-size batch (2^22 samples, 230 K triangles): properties that need no exhaustive scan"""
     from nerf_texture_b200.mesh import Mesh

@@ -13,7 +13,7 @@
 
 Samples: 8192 camera-like rays x 128 steps through the shell 0.45 <= |x| <= 0.95 around a 230 K-triangle bumpy sphere, in ray order
 (consecutive samples are neighbours in space, as they are when the renderer feeds the field).  CUDA events, median of 10, a 256 MB
-write between iterations flushes L2.  Prints `RESULT {json}`; bench.py embeds it as `mesh`."""
+write between iterations flushes L2.  `*_ray_order_ms`: the same call without visiting the batch in Morton order.  Prints `RESULT {json}`; bench.py embeds it as `mesh`."""
 import argparse
 import json
 import os
@@ -83,8 +83,11 @@ def main():
 
     res = {"samples": N, "triangles": int(len(f)), "vertices": int(len(v)), "tree_build_s": round(build_s, 3), "info": mesh.info()}
     res["trace_ms"] = timed(lambda: mesh.trace(x, dirs))
-    res["knn_ms"] = timed(lambda: mesh.knn(x, K=8))
+    res["knn_ms"] = timed(lambda: mesh.knn(x, K=8))                       # default: the batch is visited in Morton order (mesh.spatial_order)
+    res["knn_ray_order_ms"] = timed(lambda: mesh.knn(x, K=8, sort=False))
+    res["spatial_order_ms"] = timed(lambda: M.spatial_order(x))
     res["project_fused_ms"] = timed(lambda: mesh.project(x, vn_d, K=8))
+    res["project_fused_ray_order_ms"] = timed(lambda: mesh.project(x, vn_d, K=8, sort=False))
     res["project_fused_msamples_per_s"] = N / res["project_fused_ms"] / 1e3
 
     import run_reference_files as R
