@@ -198,3 +198,17 @@ def test_checkpoint_round_trip_cpu(tmp_path):
     assert not missing and not unexpected
     for k, v in b.state_dict().items():
         assert torch.equal(v, sd[k]), k
+
+
+def test_spatial_order_is_a_permutation_whatever_the_input():
+    """mesh.spatial_order only decides the order queries are visited in; it must return a permutation even for NaN / inf / identical points"""
+    import torch
+    from nerf_texture_b200.mesh import spatial_order
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(5000, 3, generator=g) * 2 - 1
+    x[5] = float("nan"); x[7, 1] = float("inf"); x[9, 2] = -float("inf")
+    for pts in (x, torch.zeros(17, 3), x[:1]):
+        o = spatial_order(pts)
+        assert sorted(o.tolist()) == list(range(len(pts)))
+    xs = x[10:][spatial_order(x[10:])]
+    assert (xs[1:] - xs[:-1]).norm(dim=1).mean() < 0.3 * (x[11:] - x[10:-1]).norm(dim=1).mean()      # neighbours in the order are neighbours in space
