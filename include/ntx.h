@@ -277,7 +277,9 @@ int ntx_mesh_knn(const void* mesh, const float* queries, uint32_t N, uint32_t K,
  * fused into one kernel: per sample the K-neighbour list stays in registers, the coarse normal of knn(use_dir_vec=True,
  * weighting='Shepard', dir_vec_wdist) is formed from `vertex_normals` [n_vertices,3] f32 (device) and both casts run back to back.
  *   -> p_sur [N,3], sdf [N] (-depth_inner if depth_inner < depth_outer else depth_outer), normal [N,3], face_idx [N] i64 (-1: neither
- *   cast hit anything within 10).  1 <= K <= 16; the mesh must have triangles. */
+ *   cast hit anything within 10).  1 <= K <= 16; the mesh must have triangles.
+ * Queries are independent and may come in any order; the kernels run one thread per query, so a batch whose neighbours in memory are
+ * neighbours in space is up to 1.6x faster (nerf_texture_b200/mesh.py orders batches of 2^19 or more along a Morton curve). */
 int ntx_mesh_project(const void* mesh, const float* vertex_normals, const float* xyz, uint32_t N, uint32_t K, float r, float dir_vec_wdist,
                      float* p_sur, float* sdf, float* normal, int64_t* face_idx, ntx_stream_t stream);
 
